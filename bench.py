@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py -- env steps/sec of the batched LOB + tile-coded TD hot path on B200.
+
+One bench "step" = one launch of the fused tick kernel: TICKS_PER_LAUNCH market ticks for every
+one of the B environments (about TICKS/K learner steps per env).  The metric is BASELINE.json's:
+env steps/sec, one env step = one experiment::serial::Learner::_step (src/experiment/serial.cpp:53-70).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs B] [--algo ...]
+
+N > 1 is launched by torchrun (one rank per GPU); envs are sharded by rank, independent policies
+need no data-path collective ("scaling": "weak").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TICKS_PER_LAUNCH = 64
+WORKLOADS = {
+    # BASELINE.json configs[1]: 4096 parallel LOBs, Q-learning tile coding, synthetic Poisson flow, 1xB200
+    "C1": dict(envs=4096, algo="q_learn", memory_size=65536),
+    # configs[2]: 65536 LOBs, SARSA(lambda)
+    "C2": dict(envs=65536, algo="sarsa", memory_size=16384),
+}
+
+
+def algorithmic_bytes_per_step(k_ticks, z_traces, double_q=False):
+    """B_step = 2*S_env + K*(B_msg + B_ring) + B_q + 28*Z with S_env=640,
+    B_msg=96, B_ring=112, B_q = 8*A*G*T*2 = 13824 (doubled for Double-Q)."""
+    return 1280.0 + 208.0 * k_ticks + (27648.0 if double_q else 13824.0) + 28.0 * z_traces
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def make_cfg(workload, n_envs, env_index0, source, args):
+    from rl_markets_b200 import abi, config
+    w = WORKLOADS[workload]
+    y = config.example_dict(**{"learning.memory_size": args.memory_size or w["memory_size"],
+                               "learning.algorithm": args.algo or w["algo"]})
+    # dt_ms = 1: 27e6 ticks per synthetic trading day, so no env reaches the close inside a bench run
+    cfg = config.from_dict(y, n_envs=n_envs, env_index0=env_index0, source=source, flow_seed=2024, dt_ms=1)
+    return y, cfg
+
+
+def run_ours(args):
+    import torch
+    from rl_markets_b200 import abi, lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOADS[args.workload]
+    B = args.envs or w["envs"]
+    y, cfg = make_cfg(args.workload, B, rank * B, abi.SOURCE_GENERATOR, args)
+    cfg.device = local
+    m = lib.BatchedMarket(cfg)
+    stream = torch.cuda.Stream()
+    m.set_stream(stream.cuda_stream)
+    ticks = args.ticks
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run (inputs = generator state, theta, traces: all in HBM)
+    for _ in range(max(args.warmup, 3)):
+        m.run_ticks(ticks)
+    m.sync()
+    c0 = m.counters()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for i in range(args.steps):
+            m.run_ticks(ticks)
+            evs[i + 1].record(stream)
+    barrier()
+    sampler.stop_flag = True
+    m.sync()
+    c1 = m.counters()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    steps_done = c1.steps - c0.steps
+    ticks_done = c1.ticks - c0.ticks
+    z_sum = c1.sum_traces - c0.sum_traces
+
+    # ---- end to end through the C ABI with HOST buffers: every launch uploads its tick messages from
+    # pinned host memory (rlm_load_ticks) and reads the per-env rewards back (rlm_get_reward)
+    e2e = None
+    if not args.no_e2e:
+        y2, cfg2 = make_cfg(args.workload, B, rank * B, abi.SOURCE_STREAM, args)
+        cfg2.device = local
+        m2 = lib.BatchedMarket(cfg2)
+        m2.set_stream(stream.cuda_stream)
+        n_chunks = max(args.warmup, 3) + args.steps
+        nbytes = ticks * B * C.sizeof(abi.TickMsg)
+        host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        gen_ticks = ticks * n_chunks
+        # synthetic messages for all envs, generated once on the host cores (not timed)
+        t_gen0 = time.time()
+        per_env = [lib.flow_generate(cfg2.flow, rank * B + b, 0, gen_ticks) for b in range(min(B, args.e2e_distinct))]
+        t_gen = time.time() - t_gen0
+        import numpy as np
+        host_np = host.numpy().view(np.uint8).reshape(ticks, B, 128)
+        env_np = [np.frombuffer(pe, dtype=np.uint8).reshape(gen_ticks, 128) for pe in per_env]
+        rew = (C.c_double * B)()
+
+        def fill(chunk):
+            for b in range(B):  # envs beyond e2e_distinct replay the stream of env (b mod distinct)
+                host_np[:, b, :] = env_np[b % len(env_np)][chunk * ticks:(chunk + 1) * ticks]
+
+        for ch in range(max(args.warmup, 3)):
+            fill(ch)
+            m2.load_ticks(host.data_ptr(), ticks)
+            m2.run_ticks(ticks)
+            m2.sync()
+        cc0 = m2.counters()
+        barrier()
+        t0 = time.perf_counter()
+        fill_s = 0.0
+        for i in range(args.steps):
+            tf0 = time.perf_counter()
+            fill(max(args.warmup, 3) + i)  # host-side staging of the next chunk (excluded below)
+            fill_s += time.perf_counter() - tf0
+            m2.load_ticks(host.data_ptr(), ticks)   # H2D inside the timed region
+            m2.run_ticks(ticks)
+            lib.check(m2.L.rlm_get_reward(m2.h, rew))  # D2H inside the timed region (syncs)
+        barrier()
+        wall = time.perf_counter() - t0 - fill_s
+        cc1 = m2.counters()
+        e2e_steps = cc1.steps - cc0.steps
+        e2e = {"steps": e2e_steps, "seconds": wall, "h2d": nbytes, "d2h": B * m2.cfg.n_state_vars * 0 + B * 8}
+        m2.close()
+
+    # ---- aggregate over ranks: max time, sum steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([total_ms, (e2e or {}).get("seconds", 0.0)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([steps_done, ticks_done, z_sum, (e2e or {}).get("steps", 0)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        total_ms = float(t[0]); steps_all, ticks_all, z_all = float(s[0]), float(s[1]), float(s[2])
+        if e2e:
+            e2e["seconds"] = float(t[1]); e2e["steps"] = float(s[3])
+    else:
+        steps_all, ticks_all, z_all = float(steps_done), float(ticks_done), float(z_sum)
+
+    if rank == 0:
+        k_bar = ticks_all / max(steps_all, 1.0)
+        z_bar = z_all / max(steps_all, 1.0)
+        is_dq = (args.algo or w["algo"]) == "double_q_learn"
+        b_step = algorithmic_bytes_per_step(k_bar, z_bar, is_dq)
+        value = steps_all / (total_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        # dominant kernel = rlm_tick_kernel (the only kernel in the timed region): per-launch numbers, rank 0
+        avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+        launch_steps = steps_done / args.steps
+        achieved = launch_steps * b_step / (avg_launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "env steps/sec (batched LOBs)", "value": value, "unit": "env_steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d parallel LOBs per GPU, %s + tile coding (32 tilings, memory_size %d per env), "
+                                   "synthetic Poisson order flow (in-kernel generator), %d ticks per launch"
+                                   % (args.workload, B, args.algo or w["algo"], args.memory_size or w["memory_size"], ticks),
+                       "envs_per_gpu": B, "ticks_per_launch": ticks, "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar,
+                       "l2": "working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * (args.memory_size or w["memory_size"]) * 8 / 1e9),
+                       "ticks_per_s": ticks_all / (total_ms * 1e-3)},
+            "gpu_launches": args.steps,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "rlm_tick_kernel",
+                         "algorithmic_bytes_per_env_step": b_step, "env_steps_per_launch": launch_steps,
+                         "avg_launch_ms": avg_launch_ms},
+        }
+        if e2e:
+            line["e2e"] = {"value": e2e["steps"] / e2e["seconds"], "unit": "env_steps/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "note": "STREAM source: rlm_load_ticks from pinned host memory + rlm_run_ticks + rlm_get_reward per launch"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_reference(args, n_procs=1, ticks=args.cpu_ticks)
+        print(json.dumps(line))
+    m.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def _ref_paths():
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    return os.path.join(ref, "ref_driver"), os.path.join(ref, "flow_csv")
+
+
+def cpu_baseline_reference(args, n_procs, ticks):
+    """Times the reference's own CPU loop: oracle/_ref/ref_driver = the UNMODIFIED reference sources
+    compiled in the build container (oracle/Makefile), one single-threaded process per env (the
+    reference's only deterministic mode, src/main.cpp:196-209), CSV parsing included, files on tmpfs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from rl_markets_b200 import config
+    drv, flow = _ref_paths()
+    w = WORKLOADS[args.workload]
+    algo = args.algo or w["algo"]
+    y = config.example_dict(**{"learning.memory_size": args.memory_size or w["memory_size"], "learning.algorithm": algo})
+    if not os.path.exists(drv):
+        # fall back to the CPU restatement ("port"), threads = n_procs
+        from rl_markets_b200 import abi
+        cfg = config.from_dict(y, n_envs=n_procs, flow_seed=2024, dt_ms=1)
+        L = oracle_lib.lib()
+        tt, secs = C.c_int64(0), C.c_double(0)
+        steps = L.lobo_run_batch(C.byref(cfg), n_procs, ticks, n_procs, C.byref(tt), C.byref(secs))
+        return {"value": steps / secs.value, "unit": "env_steps/s", "cores": n_procs, "kind": "port",
+                "sample": "%d env(s) x %d ticks through oracle/liblob_oracle.so (in-memory ticks)" % (n_procs, ticks)}
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=tmp) as d:
+        cfgp = os.path.join(d, "cfg.yaml")
+        oracle_lib.write_ref_yaml(cfgp, y)
+        procs = []
+        for i in range(n_procs):
+            md, tas = os.path.join(d, "e%d_md_1.csv" % i), os.path.join(d, "e%d_tas_1.csv" % i)
+            subprocess.check_call([flow, "--seed", "2024", "--env", str(i), "--ticks", str(ticks), "--dt-ms", "1", "--md", md, "--tas", tas])
+        t0 = time.perf_counter()
+        for i in range(n_procs):
+            md, tas = os.path.join(d, "e%d_md_1.csv" % i), os.path.join(d, "e%d_tas_1.csv" % i)
+            procs.append(subprocess.Popen([drv, "--config", cfgp, "--md", md, "--tas", tas], stdout=subprocess.PIPE))
+        outs = [p.communicate()[0] for p in procs]
+        wall = time.perf_counter() - t0
+    steps = 0
+    inner = 0.0
+    for o in outs:
+        s = json.loads(o.decode().strip().splitlines()[-1])
+        steps += s["steps"]
+        inner = max(inner, s["seconds"])
+    return {"value": steps / inner, "unit": "env_steps/s", "cores": n_procs, "kind": "reference",
+            "sample": "%d process(es) x %d synthetic ticks (%d learner steps), %s, CSV parsing included, "
+                      "timed inside ref_driver (max over processes %.2fs; wall incl. process start %.2fs)"
+                      % (n_procs, ticks, steps, algo, inner, wall)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_procs = os.cpu_count() or 1
+    vals = []
+    last = None
+    for i in range(max(args.warmup, 0) + args.steps):
+        last = cpu_baseline_reference(args, n_procs=n_procs, ticks=args.ref_ticks)
+        if i >= args.warmup:
+            vals.append(last)
+    value = sum(v["value"] for v in vals) / len(vals)
+    w = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "env steps/sec (batched LOBs)", "value": value, "unit": "env_steps/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "%s: %s + tile coding (memory_size %d per env), synthetic Poisson order flow; reference arm = "
+                                   "%d independent single-threaded reference processes on the host cores"
+                                   % (args.workload, args.algo or w["algo"], args.memory_size or w["memory_size"], n_procs)},
+            "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": n_procs, "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C1", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0)
+    ap.add_argument("--algo", default="")
+    ap.add_argument("--memory-size", dest="memory_size", type=int, default=0)
+    ap.add_argument("--ticks", type=int, default=TICKS_PER_LAUNCH)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-distinct", type=int, default=64, help="distinct host-generated streams replayed across envs in the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-ticks", type=int, default=400000)
+    ap.add_argument("--ref-ticks", type=int, default=200000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

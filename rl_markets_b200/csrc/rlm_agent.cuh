@@ -1,0 +1,328 @@
+// rlm_agent.cuh -- warp-cooperative tile-coded TD agent (one warp per env, lane j = tiling j).
+//
+// Restates, for N_TILINGS == 32 == warp width:
+//   tiles()/hash_UNH        src/rl/tiles.cpp:31-75,130-169
+//   State::populateFeatures src/rl/state.cpp:53-65
+//   Agent::getQ/argmaxQ     src/rl/agent.cpp:117-174   (DoubleAgent :202-264)
+//   Traces                  src/rl/traces.cpp:30-101
+//   QLearn/SARSA/DoubleQLearn UpdateTraces/UpdateWeights  src/rl/agent.cpp:268-353
+//   Greedy/EpsilonGreedy/Random::Sample  src/rl/policy.cpp:27-75
+//   std::mt19937_64, uniform_real/int_distribution (libstdc++ 13), glibc rand()
+#pragma once
+#include "rlm_env.cuh"
+
+#define FULL 0xffffffffu
+#define HS_SLOTS 512
+#define HS_EMPTY (-1)
+
+// ------------------------------------------------------------------ RNGs (lane 0)
+// std::mt19937_64, regenerated one word at a time: equivalent to the batch twist of
+// libstdc++'s _M_gen_rand because word k only depends on old x[k], old-or-new x[k+1] and
+// x[k+156 mod 312] exactly as they stand when the batch loop reaches k.
+__device__ unsigned long long mt_next(unsigned long long* x, int& p) {
+  int k = p; if (k >= 312) k -= 312;   // _M_p == 312 means "regenerate": start at word 0
+  const unsigned long long UM = 0xFFFFFFFF80000000ull, LM = 0x7FFFFFFFull, A = 0xB5026F5AA96619E9ull;
+  int k1 = k + 1; if (k1 == 312) k1 = 0;
+  int km = k + 156; if (km >= 312) km -= 312;
+  unsigned long long y = (x[k] & UM) | (x[k1] & LM);
+  unsigned long long z = x[km] ^ (y >> 1) ^ ((y & 1ull) ? A : 0ull);
+  x[k] = z;
+  p = k + 1;   // stays in 1..312; 312 wraps on the next call
+  z ^= (z >> 29) & 0x5555555555555555ull;
+  z ^= (z << 17) & 0x71D67FFFEDA60000ull;
+  z ^= (z << 37) & 0xFFF7EEE000000000ull;
+  z ^= z >> 43;
+  return z;
+}
+// generate_canonical<double,53> on a 64-bit URBG + uniform_real_distribution(0,1)
+__device__ double mt_uniform_real(unsigned long long* x, int& p) {
+  double r = __ull2double_rn(mt_next(x, p)) / 18446744073709551616.0;
+  if (r >= 1.0) r = 0.99999999999999988897769753748;  // nextafter(1,0)
+  return r * (1.0 - 0.0) + 0.0;
+}
+// uniform_int_distribution<unsigned>(0,n-1): Lemire with a 128-bit product
+__device__ unsigned mt_uniform_int(unsigned long long* x, int& p, unsigned n) {
+  unsigned long long range = n;
+  unsigned long long g = mt_next(x, p);
+  unsigned long long low = g * range, hi = __umul64hi(g, range);
+  if (low < range) {
+    unsigned long long threshold = (0ull - range) % range;
+    while (low < threshold) {
+      g = mt_next(x, p);
+      low = g * range; hi = __umul64hi(g, range);
+    }
+  }
+  return (unsigned)hi;
+}
+// glibc rand() (random_r TYPE_3)
+__device__ int crand_next(EnvHdr& e) {
+  unsigned v = (unsigned)e.crand_r[e.crand_f] + (unsigned)e.crand_r[e.crand_b];
+  e.crand_r[e.crand_f] = (int)v;
+  int out = (int)(v >> 1);
+  e.crand_f = e.crand_f + 1 == 31 ? 0 : e.crand_f + 1;
+  e.crand_b = e.crand_b + 1 == 31 ? 0 : e.crand_b + 1;
+  return out;
+}
+
+// ------------------------------------------------------------------ windows (lane w = window w)
+// Accumulator<double>::push / RollingMean<double>::push (accumulators.cpp:17-27,86-109)
+__device__ __forceinline__ void window_push(EnvHdr& e, double* ring, int w, double val) {
+  const int ws = P.win_size[w];
+  double* r = ring + P.win_off[w];
+  int head = e.w_head[w], cnt = e.w_count[w];
+  double sum = e.w_sum[w], mean = e.w_mean[w], s = e.w_s[w];
+  const bool overflow = (cnt == ws);
+  const double old = r[head];  // oldest element when full
+  r[head] = val;
+  head = head + 1 == ws ? 0 : head + 1;
+  sum += val;
+  double n = (double)(cnt + 1);
+  double old_mean = mean;
+  mean += (val - mean) / n;
+  s += (val - mean) * (val - old_mean);
+  if (overflow) {
+    sum -= old;
+    double n2 = (double)ws;
+    double old_mean2 = mean;
+    mean -= (old - mean) / n2;
+    s -= (old - mean) * (old - old_mean2);
+  } else {
+    cnt += 1;
+  }
+  e.w_head[w] = head; e.w_count[w] = cnt; e.w_sum[w] = sum; e.w_mean[w] = mean; e.w_s[w] = s;
+}
+
+// ------------------------------------------------------------------ tile coding
+__device__ __forceinline__ int mod_m(unsigned long long sum) {  // (int)(sum % m), sum < 2^36
+  if (P.m_pow2) return (int)(sum & (unsigned long long)(P.memory_size - 1));
+  unsigned long long q = __umul64hi(sum, P.m_magic);
+  unsigned long long r = sum - q * (unsigned long long)P.memory_size;
+  while (r >= (unsigned long long)P.memory_size) r -= (unsigned long long)P.memory_size;
+  return (int)r;
+}
+
+// coordinate of tiling j for quantised value q at dimension i (tiles.cpp:56-63): base = j*(1+2i)
+__device__ __forceinline__ int tile_coord(int q, int i, int j) {
+  int base = j * (1 + 2 * i);
+  if (q >= base) return q - ((q - base) % RLM_N_TILINGS);
+  return q + 1 + ((base - q - 1) % RLM_N_TILINGS) - RLM_N_TILINGS;
+}
+
+// Partial hash sum (everything except the action-dependent integer) for lane j's tiling of one
+// feature group: floats vars[0..nf) then the tiling index (tiles.cpp:65-68, hash_UNH :152-161).
+__device__ __forceinline__ unsigned long long tile_base_sum(const unsigned* rnd, const float* vars, int nf, int j) {
+  unsigned long long sum = 0;
+  for (int i = 0; i < nf; ++i) {
+    int q = (int)floorf(vars[i] * (float)RLM_N_TILINGS);
+    int c = tile_coord(q, i, j);
+    sum += rnd[(c + 449 * i) & 2047];
+  }
+  sum += rnd[(j + 449 * nf) & 2047];
+  return sum;
+}
+__device__ __forceinline__ int tile_index(const unsigned* rnd, unsigned long long base, int nf, int h1) {
+  return mod_m(base + rnd[(h1 + 449 * (nf + 1)) & 2047]);
+}
+
+// Exact-order Q(s,a) for all actions (agent.cpp:117-135): lanes gather theta for their tiling,
+// values are transposed through shared memory and lanes 0..A-1 accumulate
+//   Q += w0*th[f_i] (i<T);  Q += w1*th[f_i] (T<=i<2T);  Q += w2*th[f_i] (T<=i<3T)
+// strictly left to right, so the result is bitwise the reference's.
+// vars: state variables (n of them) in shared memory; vbuf: >= 2*A*32 doubles of scratch.
+// If null_state, every feature index is 0 (the never-populated State of serial.cpp:14-15,55).
+__device__ void eval_q(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
+                       bool null_state, double* vbuf, int lane, double& qa_out, double& qb_out) {
+  const int A = P.n_actions;
+  double qa = 0.0, qb = 0.0;
+  double* va = vbuf;
+  double* vb = vbuf + RLM_MAX_ACTIONS * 32;
+#pragma unroll 1
+  for (int g = 0; g < 3; ++g) {
+    const float* gv = (g == 1) ? vars + 3 : vars;
+    const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
+    unsigned long long base = null_state ? 0ull : tile_base_sum(rnd, gv, nf, lane);
+    double ta[RLM_MAX_ACTIONS], tb[RLM_MAX_ACTIONS];
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+      if (a < A) {
+        int f = null_state ? 0 : tile_index(rnd, base, nf, g * A + a);
+        ta[a] = th_a[f];
+        if (th_b) tb[a] = th_b[f];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+      if (a < A) {
+        va[a * 32 + lane] = ta[a];
+        if (th_b) vb[a * 32 + lane] = tb[a];
+      }
+    }
+    __syncwarp();
+    if (lane < A) {
+      const double* ra = va + lane * 32;
+      const double* rb = vb + lane * 32;
+      if (g == 0) {
+        const double w = P.gw[0];
+        for (int i = 0; i < 32; ++i) qa += w * ra[i];
+        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
+      } else if (g == 1) {
+        double w = P.gw[1];
+        for (int i = 0; i < 32; ++i) qa += w * ra[i];
+        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
+        w = P.gw[2];  // the third loop starts at T, not 2T
+        for (int i = 0; i < 32; ++i) qa += w * ra[i];
+        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
+      } else {
+        const double w = P.gw[2];
+        for (int i = 0; i < 32; ++i) qa += w * ra[i];
+        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
+      }
+    }
+    __syncwarp();
+  }
+  qa_out = qa;
+  qb_out = qb;
+}
+
+// argmax with rand() tie-breaks over q[0..A) (agent.cpp:144-169); lane 0
+__device__ int argmax_ties(EnvHdr& e, const double* q) {
+  int index = 0, n_ties = 1;
+  double cur = q[0];
+  for (int a = 1; a < P.n_actions; a++) {
+    double val = q[a];
+    if (val >= cur) {
+      if (val > cur) { cur = val; index = a; }
+      else {
+        n_ties++;
+        if (0 == crand_next(e) % n_ties) { cur = val; index = a; }
+      }
+    }
+  }
+  return index;
+}
+// Greedy::Sample (policy.cpp:37-55); lane 0
+__device__ int greedy_sample(EnvHdr& e, const double* qs) {
+  int argmax = 0, n_ties = 1;
+  for (int a = 1; a < P.n_actions; a++) {
+    if (qs[a] > qs[argmax]) argmax = a;
+    else if (qs[a] >= qs[argmax]) {
+      n_ties++;
+      if (0 == crand_next(e) % n_ties) argmax = a;
+    }
+  }
+  return argmax;
+}
+// Agent::action / DoubleAgent::action + Policy::Sample; lane 0.  qa/qb: Q_A(s,.), Q_B(s,.)
+__device__ int policy_action(EnvHdr& e, const double* qa, const double* qb, unsigned long long* mt, const DynParams& D) {
+  double qs[RLM_MAX_ACTIONS];
+  for (int a = 0; a < P.n_actions; ++a) qs[a] = P.is_double ? (qa[a] + qb[a]) / 2.0 : qa[a];
+  int pt = D.greedy ? RLM_POLICY_GREEDY : P.policy_type;
+  if (pt == RLM_POLICY_RANDOM) return (int)mt_uniform_int(mt, e.mt_pol_idx, (unsigned)P.n_actions);
+  if (pt == RLM_POLICY_EPSILON_GREEDY) {
+    if (mt_uniform_real(mt, e.mt_pol_idx) < D.eps) return (int)mt_uniform_int(mt, e.mt_pol_idx, (unsigned)P.n_actions);
+  }
+  return greedy_sample(e, qs);
+}
+
+// ------------------------------------------------------------------ traces + weight update
+// The reference keeps a dense float e[M] plus a nonzero list (traces.cpp); here only the list
+// exists: (f, e) pairs, compact, per env.  One fused pass implements, in the reference's order,
+//   Traces::decay(rate)            e *= rate; drop if e < 0.01                       traces.cpp:30-38
+//   Traces::update(from, action)   for a = 0..A-1: clear / set the 32 group-0 tiles   traces.cpp:40-50
+//   Agent::updateQ(alpha*delta)    theta[f] += (alpha*delta/32) * e[f]                agent.cpp:137-142
+// update()'s outcome for a feature f touched by it is decided by the LAST action whose tile list
+// contains f (set if that action is the one taken, cleared otherwise); a small open-addressed
+// hash set in shared memory maps f -> last such action.
+__device__ __forceinline__ unsigned hs_hash(int f) { return ((unsigned)f * 2654435761u) >> 23; }  // 9 bits
+
+__device__ int trace_pass(EnvHdr& e, const unsigned* rnd, int* hs_keys, int* hs_vals, int* tf, float* te,
+                          double* theta, int action, float rate, double scaled_update, int lane) {
+  const int A = P.n_actions;
+  // group-0 tiles of the from-state for every action (state.cpp:55-57)
+  int F[RLM_MAX_ACTIONS];
+  {
+    unsigned long long base = e.null_from ? 0ull : tile_base_sum(rnd, e.from_vars, 3, lane);
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) F[a] = (a < A) ? (e.null_from ? 0 : tile_index(rnd, base, 3, a)) : 0;
+  }
+  for (int i = lane; i < HS_SLOTS; i += 32) { hs_keys[i] = HS_EMPTY; hs_vals[i] = -1; }
+  __syncwarp();
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+    if (a < A) {
+      unsigned slot = hs_hash(F[a]);
+      while (true) {
+        int old = atomicCAS(&hs_keys[slot], HS_EMPTY, F[a]);
+        if (old == HS_EMPTY || old == F[a]) { atomicMax(&hs_vals[slot], a); break; }
+        slot = (slot + 1) & (HS_SLOTS - 1);
+      }
+    }
+  }
+  __syncwarp();
+  auto lookup = [&](int f) -> int {  // last action touching f, or -1
+    unsigned slot = hs_hash(f);
+    while (true) {
+      int k = hs_keys[slot];
+      if (k == f) return hs_vals[slot];
+      if (k == HS_EMPTY) return -1;
+      slot = (slot + 1) & (HS_SLOTS - 1);
+    }
+  };
+  const float tol = 0.01f;
+  int w = 0;
+  if (rate != 0.0f) {
+    const int n = e.n_traces;
+    for (int base = 0; base < n; base += 32) {
+      int i = base + lane;
+      bool valid = i < n;
+      int f = valid ? tf[i] : 0;
+      float ev = valid ? te[i] : 0.0f;
+      ev *= rate;
+      bool keep = valid && !(ev < tol) && (lookup(f) < 0);
+      unsigned mask = __ballot_sync(FULL, keep);
+      int pos = w + __popc(mask & ((1u << lane) - 1u));
+      if (keep) {
+        tf[pos] = f;
+        te[pos] = ev;
+        theta[f] += scaled_update * (double)ev;
+      }
+      w += __popc(mask);
+    }
+  }
+  // set(): the taken action's tiles that no later action cleared; one entry per distinct f
+  {
+    int f = F[0];
+#pragma unroll
+    for (int a = 1; a < RLM_MAX_ACTIONS; ++a) if (a == action) f = F[a];
+    bool add = (lookup(f) == action);
+    unsigned same = __match_any_sync(FULL, f);
+    add = add && ((__ffs(same) - 1) == lane);
+    unsigned mask = __ballot_sync(FULL, add);
+    int pos = w + __popc(mask & ((1u << lane) - 1u));
+    int total = w + __popc(mask);
+    if (total > P.trace_cap) {
+      if (lane == 0) e.err |= ERR_TRACE_OVERFLOW;
+      add = add && (pos < P.trace_cap);
+      total = P.trace_cap;
+    }
+    if (add) {
+      tf[pos] = f;
+      te[pos] = 1.0f;
+      theta[f] += scaled_update * (double)1.0f;
+    }
+    w = total;
+  }
+  __syncwarp();
+  return w;
+}
+
+// order-independent hash of {(f, e, theta[f])} for the parity record
+__device__ unsigned long long trace_hash(const int* tf, const float* te, const double* theta, int n, int lane) {
+  unsigned long long h = 0;
+  for (int i = lane; i < n; i += 32) {
+    int f = tf[i];
+    h += rlm_trace_mix((unsigned)f, __float_as_uint(te[i]), (unsigned long long)__double_as_longlong(theta[f]));
+  }
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(FULL, h, o);
+  return h;
+}

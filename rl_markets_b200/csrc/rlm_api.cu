@@ -1,0 +1,572 @@
+// rlm_api.cu -- host side of the C ABI declared in include/rlm.h.
+//
+// Owns device memory, derives the constant tables the kernels need (venue tick chains,
+// window layout, modulo magic), and maps the reference's exception classes to rlm_status
+// codes.  There is deliberately NO CPU execution path here: without a CUDA device
+// rlm_create fails with RLM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "rlm.h"
+#include "rlm_flow_tables.h"
+#include "rlm_kernels.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) return fail((_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? RLM_ERR_NO_DEVICE : RLM_ERR_CUDA, \
+                                       std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+struct rlm_handle_s {
+  rlm_config cfg;
+  DevParams hp;
+  DevPtrs ptr;
+  DynParams dyn;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int warps = 14;
+  int n_policies = 1;
+  size_t env_bytes = 0;
+  rlm_tick_msg* d_stream = nullptr;
+  size_t stream_cap = 0;  // messages
+  int stream_ticks = 0, stream_cursor = 0;
+  long long launches = 0;
+  double alpha = 0, eps = 0;
+};
+
+static const rlm_handle_s* g_params_owner = nullptr;
+
+extern "C" {
+
+const char* rlm_last_error(void) { return g_err.c_str(); }
+int rlm_abi_version(void) { return RLM_ABI_VERSION; }
+
+int rlm_config_default(rlm_config* c) {
+  if (!c) return fail(RLM_ERR_INVALID_ARGUMENT, "null config");
+  memset(c, 0, sizeof(*c));
+  c->n_envs = 1; c->device = 0; c->env_index0 = 0; c->shared_policy = 0; c->source = RLM_SOURCE_GENERATOR;
+  // config/example.yaml
+  c->memory_size = 20000000; c->n_tilings = 32; c->n_actions = 9; c->algorithm = RLM_ALGO_DOUBLE_Q_LEARN;
+  c->group_weights[0] = 0.65; c->group_weights[1] = 0.25; c->group_weights[2] = 0.10;
+  c->gamma = 0.975; c->lambda = 0.85; c->omega = 1.0; c->alpha_start = 0.001; c->alpha_floor = 0.001; c->beta = 0.005;
+  c->policy_type = RLM_POLICY_EPSILON_GREEDY; c->eps_init = 0.8f; c->eps_floor = 0.0001f; c->eps_T = 800;
+  c->tau_init = 1.0f; c->tau_floor = 1.0f; c->tau_T = 1;
+  c->spread_lookback = 45;
+  c->reward_measure = RLM_REWARD_PNL_DAMPED; c->damping_factor = 0.15f; c->pos_weight = 0.0f; c->trd_weight = 0.0f; c->pnl_weight = 1.0f;
+  c->pnl_lookback = 0;
+  const int vars[8] = {RLM_VAR_POS, RLM_VAR_A_DIST, RLM_VAR_B_DIST, RLM_VAR_MPM, RLM_VAR_SPD, RLM_VAR_VOL, RLM_VAR_IMB, RLM_VAR_SVL};
+  c->n_state_vars = 8;
+  for (int i = 0; i < 8; ++i) c->state_vars[i] = vars[i];
+  c->lb_mpm = 15; c->lb_vlt = 60; c->lb_svl = 60; c->lb_rsi = 0; c->lb_vwap = 0;
+  c->pos_lb = -50; c->pos_ub = 50; c->order_size = 10;
+  c->target_price_type = RLM_TP_YAML_MIDPRICE; c->tp_lookback = 1;
+  // LondonStockExchange, symbol group of AAL (src/market/market.cpp:206-227)
+  const double px[10] = {0., 1., 5., 10., 50., 100., 500., 1000., 5000., 10000.};
+  const double ts[10] = {0.0001, 0.0005, 0.001, 0.005, 0.01, 0.05, 0.1, 0.5, 1, 5};
+  c->n_bands = 10;
+  for (int i = 0; i < 10; ++i) { c->band_px[i] = px[i]; c->band_ts[i] = ts[i]; }
+  c->open_ms = 8LL * 3600000; c->close_ms = 16LL * 3600000 + 30LL * 60000;
+  c->random_seed = 1994;
+  rlm_flow_default_params(&c->flow, 1, 250);
+  return RLM_OK;
+}
+
+static int derive(rlm_handle_s* h) {
+  const rlm_config& c = h->cfg;
+  DevParams& p = h->hp;
+  memset(&p, 0, sizeof(p));
+  if (c.n_envs <= 0) return fail(RLM_ERR_INVALID_ARGUMENT, "n_envs must be positive");
+  if (c.n_tilings != RLM_N_TILINGS) return fail(RLM_ERR_UNSUPPORTED, "the B200 path maps tiling j to lane j: n_tilings must be 32");
+  if (c.n_actions < 1 || c.n_actions > RLM_MAX_ACTIONS) return fail(RLM_ERR_UNSUPPORTED, "n_actions must be in 1..9 (Intraday::DoAction has 9 actions)");
+  if (c.algorithm != RLM_ALGO_Q_LEARN && c.algorithm != RLM_ALGO_SARSA && c.algorithm != RLM_ALGO_DOUBLE_Q_LEARN)
+    return fail(RLM_ERR_UNSUPPORTED, "algorithm not built yet: q_learn, sarsa, double_q_learn are (R-learning variants: SURVEY 8f)");
+  if (c.policy_type != RLM_POLICY_GREEDY && c.policy_type != RLM_POLICY_RANDOM && c.policy_type != RLM_POLICY_EPSILON_GREEDY)
+    return fail(RLM_ERR_UNSUPPORTED, "policy not built yet: greedy, random, epsilon_greedy are (boltzmann: SURVEY 8f)");
+  if (c.memory_size < 1 || c.memory_size > 2147483647LL) return fail(RLM_ERR_INVALID_ARGUMENT, "memory_size must fit the reference's int tile index");
+  if (c.n_state_vars < 4 || c.n_state_vars > RLM_N_STATE_MAX) return fail(RLM_ERR_INVALID_ARGUMENT, "state.variables needs 4..13 entries (State::populateFeatures splits at 3)");
+  if (c.n_bands < 1 || c.n_bands > RLM_MAX_BANDS) return fail(RLM_ERR_INVALID_ARGUMENT, "bad venue table");
+  if (c.order_size <= 0) return fail(RLM_ERR_RUNTIME, "Order size must be non-zero and positive.");
+  if (c.tp_lookback < 1) return fail(RLM_ERR_INVALID_ARGUMENT, "target_price.lookback must be >= 1");
+  if (c.shared_policy) return fail(RLM_ERR_UNSUPPORTED, "shared_policy is not built yet in this round");
+  p.n_envs = c.n_envs; p.n_actions = c.n_actions; p.algorithm = c.algorithm; p.policy_type = c.policy_type;
+  p.reward_measure = c.reward_measure; p.n_state_vars = c.n_state_vars;
+  for (int i = 0; i < c.n_state_vars; ++i) {
+    if (c.state_vars[i] < 0 || c.state_vars[i] > RLM_VAR_LAST_ACTION) return fail(RLM_ERR_INVALID_ARGUMENT, "Unknown state variable");
+    p.state_vars[i] = c.state_vars[i];
+  }
+  // inverted selector of base.cpp:101-112: yaml "midprice" -> tp::MicroPrice, anything else -> tp::MidPrice
+  p.tp_is_micro = (c.target_price_type == RLM_TP_YAML_MIDPRICE) ? 1 : 0;
+  p.l2p_book = (c.target_price_type == RLM_TP_YAML_BOOK) ? 1 : 0;  // intraday.cpp:64
+  p.order_size = c.order_size; p.source = c.source; p.shared_policy = c.shared_policy;
+  p.is_double = (c.algorithm == RLM_ALGO_DOUBLE_Q_LEARN) ? 1 : 0;
+  p.pos_lb = c.pos_lb; p.pos_ub = c.pos_ub; p.memory_size = c.memory_size;
+  p.m_pow2 = ((c.memory_size & (c.memory_size - 1)) == 0) ? 1 : 0;
+  p.m_magic = (unsigned long long)((((unsigned __int128)1) << 64) / (unsigned __int128)c.memory_size);
+  if (c.memory_size == 1) p.m_magic = ~0ull;
+  p.gl = (float)(c.gamma * c.lambda);  // Traces::decay(float rate) narrows gamma*lambda (A11)
+  for (int i = 0; i < 3; ++i) p.gw[i] = c.group_weights[i];
+  p.gamma = c.gamma;
+  p.damping = c.damping_factor; p.pos_weight = c.pos_weight; p.trd_weight = c.trd_weight; p.pnl_weight = c.pnl_weight;
+  p.ewma_alpha = 2.0 / (std::max(c.lb_rsi, 1) + 1.0);  // accumulators.cpp:149-154
+  // windows: base.cpp:35-50 (max(lookback,1)) + target price lookback
+  int ws[RLM_NWIN];
+  ws[W_MID] = std::max(c.lb_mpm, 1); ws[W_VLT] = std::max(c.lb_vlt, 1);
+  ws[W_VNUM] = std::max(c.lb_vwap, 1); ws[W_VDEN] = std::max(c.lb_vwap, 1);
+  ws[W_SPREAD] = std::max(c.spread_lookback, 1); ws[W_TP] = c.tp_lookback;
+  ws[W_ASKTX] = std::max(c.lb_svl, 1); ws[W_BIDTX] = std::max(c.lb_svl, 1);
+  ws[W_PNLUP] = std::max(c.pnl_lookback, 1); ws[W_PNLDN] = std::max(c.pnl_lookback, 1);
+  int off = 0;
+  for (int w = 0; w < RLM_NWIN; ++w) { p.win_size[w] = ws[w]; p.win_off[w] = off; off += ws[w]; }
+  p.ring_total = off;
+  p.env_stride = (int)((sizeof(EnvHdr) + (size_t)off * 8 + 15) & ~(size_t)15);
+  // trace capacity: an entry survives k decays while (gamma*lambda)^k >= 0.01 (traces.cpp:30-38)
+  int cap = c.trace_cap;
+  if (cap <= 0) {
+    double gl = (double)p.gl;
+    int life = 1;
+    if (gl > 0.0 && gl < 1.0) life = (int)ceil(log(0.01) / log(gl)) + 1;
+    else if (gl >= 1.0) return fail(RLM_ERR_UNSUPPORTED, "gamma*lambda >= 1 needs an explicit trace_cap");
+    cap = RLM_N_TILINGS * (life + 1);
+    if (cap > 100000) return fail(RLM_ERR_UNSUPPORTED, "derived trace_cap exceeds MAX_NONZERO_TRACES (traces.h:10); set trace_cap");
+  }
+  p.trace_cap = (cap + 31) & ~31;
+  p.record_envs = std::min(std::max(c.record_envs, 0), c.n_envs);
+  p.record_cap = std::max(c.record_cap, 0);
+  p.env_index0 = c.env_index0;
+  p.flow = c.flow;
+  // ---- venue chains (src/market/market.cpp:27-37, 78-128), same fp64 operation order as the reference
+  VenueD& v = p.venue;
+  v.n = c.n_bands;
+  for (int i = 0; i < c.n_bands; ++i) {
+    v.px[i] = c.band_px[i]; v.ts[i] = c.band_ts[i];
+    if (i > 0 && !(c.band_px[i] > c.band_px[i - 1])) return fail(RLM_ERR_INVALID_ARGUMENT, "venue bands must ascend");
+    if (!(c.band_ts[i] > 0)) return fail(RLM_ERR_INVALID_ARGUMENT, "venue tick sizes must be positive");
+  }
+  {
+    int ticks = 0;
+    v.cum_full[0] = 0;
+    for (int i = 0; i + 1 < v.n; ++i) {
+      volatile double q = (v.px[i + 1] - v.px[i]) / v.ts[i];
+      ticks = (int)((double)ticks + q);  // `int += double`
+      v.cum_full[i + 1] = ticks;
+    }
+    long acc = 0;
+    v.tts_tick[0] = 0;
+    for (int i = 1; i < v.n; ++i) {
+      volatile double q = (v.px[i] - v.px[i - 1]) / v.ts[i - 1];
+      acc = (long)((double)acc + q);  // `long += double`
+      v.tts_tick[i] = (int)acc;
+    }
+    double price = 0;
+    v.cum_price[0] = 0.0;
+    for (int i = 0; i + 1 < v.n; ++i) {
+      volatile double prod = ((double)v.tts_tick[i + 1] - (double)v.tts_tick[i]) * v.ts[i];
+      price += prod;
+      v.cum_price[i + 1] = price;
+    }
+  }
+  v.open_lo = c.open_ms + 30LL * 60000; v.close_hi = c.close_ms - 30LL * 60000;
+  return RLM_OK;
+}
+
+static int upload_params(rlm_handle_s* h) {
+  if (g_params_owner != h) {
+    CK(rlm_upload_params(&h->hp));
+    g_params_owner = h;
+  }
+  return RLM_OK;
+}
+
+int rlm_create(const rlm_config* cfg, rlm_handle* out) {
+  if (!cfg || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(RLM_ERR_NO_DEVICE, std::string("no CUDA device: ") + (ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce)) +
+                                       " (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(RLM_ERR_INVALID_ARGUMENT, "bad device ordinal");
+  rlm_handle_s* h = new rlm_handle_s();
+  h->cfg = *cfg;
+  int rc = derive(h);
+  if (rc != RLM_OK) { delete h; return rc; }
+  CK(cudaSetDevice(cfg->device));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const DevParams& p = h->hp;
+  h->n_policies = cfg->shared_policy ? 1 : cfg->n_envs;
+  h->env_bytes = (size_t)p.env_stride * cfg->n_envs;
+  memset(&h->ptr, 0, sizeof(h->ptr));
+  CK(cudaMalloc(&h->ptr.env, h->env_bytes));
+  size_t th_bytes = (size_t)h->n_policies * (size_t)p.memory_size * 8;
+  CK(cudaMalloc(&h->ptr.theta, th_bytes));
+  CK(cudaMemsetAsync(h->ptr.theta, 0, th_bytes, h->stream));
+  if (p.is_double) {
+    CK(cudaMalloc(&h->ptr.theta_b, th_bytes));
+    CK(cudaMemsetAsync(h->ptr.theta_b, 0, th_bytes, h->stream));
+  }
+  CK(cudaMalloc(&h->ptr.trace_f, (size_t)cfg->n_envs * p.trace_cap * 4));
+  CK(cudaMalloc(&h->ptr.trace_e, (size_t)cfg->n_envs * p.trace_cap * 4));
+  CK(cudaMalloc(&h->ptr.mt_pol, (size_t)cfg->n_envs * 312 * 8));
+  if (p.is_double || cfg->random_init) CK(cudaMalloc(&h->ptr.mt_agt, (size_t)cfg->n_envs * 312 * 8));
+  if (p.record_envs > 0 && p.record_cap > 0) {
+    CK(cudaMalloc(&h->ptr.records, (size_t)p.record_envs * p.record_cap * sizeof(rlm_step_record)));
+    CK(cudaMalloc(&h->ptr.record_count, (size_t)p.record_envs * 4));
+    CK(cudaMemsetAsync(h->ptr.record_count, 0, (size_t)p.record_envs * 4, h->stream));
+  } else {
+    h->hp.record_envs = 0;
+  }
+  CK(cudaMalloc(&h->ptr.counters, 8 * 8));
+  CK(cudaMemsetAsync(h->ptr.counters, 0, 8 * 8, h->stream));
+  g_params_owner = nullptr;
+  rc = upload_params(h);
+  if (rc != RLM_OK) return rc;
+  CK(rlm_launch_init(h->ptr, cfg->n_envs, 0, h->stream));
+  CK(rlm_launch_seed(h->ptr, cfg->n_envs, cfg->random_seed, h->stream));
+  if (cfg->random_init) CK(rlm_launch_random_init(h->ptr, h->n_policies, h->stream));
+  // Agent ctor: alpha(alpha_start) (agent.cpp:25); EpsilonGreedy ctor: eps(eps) (policy.cpp:63, main.cpp:149-154)
+  h->alpha = cfg->alpha_start;
+  h->eps = (double)cfg->eps_init;
+  memset(&h->dyn, 0, sizeof(h->dyn));
+  // 14 warps per CTA, 2 CTAs per SM: 28 envs per SM, so 4096 envs are one wave of 148 SMs
+  h->warps = 14;
+  {
+    int dev_smem = 0;
+    CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    while (h->warps > 4 && rlm_smem_bytes(h->warps, p.env_stride) > (size_t)dev_smem) h->warps = (h->warps == 14) ? 8 : 4;
+    if (rlm_smem_bytes(h->warps, p.env_stride) > (size_t)dev_smem)
+      return fail(RLM_ERR_UNSUPPORTED, "window lookbacks too large for shared memory staging");
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return RLM_OK;
+}
+
+int rlm_destroy(rlm_handle h) {
+  if (!h) return RLM_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->ptr.env); cudaFree(h->ptr.theta); cudaFree(h->ptr.theta_b); cudaFree(h->ptr.dtheta);
+  cudaFree(h->ptr.trace_f); cudaFree(h->ptr.trace_e); cudaFree(h->ptr.mt_pol); cudaFree(h->ptr.mt_agt);
+  cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters); cudaFree(h->d_stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (g_params_owner == h) g_params_owner = nullptr;
+  delete h;
+  return RLM_OK;
+}
+
+int rlm_set_stream(rlm_handle h, void* cuda_stream) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  return RLM_OK;
+}
+
+int rlm_reset(rlm_handle h) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = upload_params(h);
+  if (rc) return rc;
+  CK(rlm_launch_init(h->ptr, h->cfg.n_envs, 1, h->stream));
+  h->stream_cursor = 0; h->stream_ticks = 0;
+  return RLM_OK;
+}
+
+int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks) {
+  if (!h || !msgs || n_ticks <= 0) return fail(RLM_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (h->cfg.source != RLM_SOURCE_STREAM) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was created with source = generator");
+  CK(cudaSetDevice(h->cfg.device));
+  size_t n = (size_t)n_ticks * h->cfg.n_envs;
+  if (n > h->stream_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_stream);
+    h->d_stream = nullptr;
+    CK(cudaMalloc(&h->d_stream, n * sizeof(rlm_tick_msg)));
+    h->stream_cap = n;
+  }
+  CK(cudaMemcpyAsync(h->d_stream, msgs, n * sizeof(rlm_tick_msg), cudaMemcpyHostToDevice, h->stream));
+  h->ptr.stream = h->d_stream;
+  h->stream_ticks = n_ticks;
+  h->stream_cursor = 0;
+  return RLM_OK;
+}
+
+int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
+  if (!h || n_ticks < 0) return fail(RLM_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (n_ticks == 0) return RLM_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = upload_params(h);
+  if (rc) return rc;
+  DynParams d = h->dyn;
+  d.alpha = h->alpha; d.eps = h->eps; d.n_ticks = n_ticks;
+  if (h->cfg.source == RLM_SOURCE_STREAM) {
+    if (h->stream_cursor + n_ticks > h->stream_ticks)
+      return fail(RLM_ERR_END_OF_DATA, "rlm_run_ticks: not enough ticks loaded (performAction would return false, base.cpp:289)");
+    d.stream_off = h->stream_cursor;
+    d.stream_ticks = h->stream_ticks;
+    h->stream_cursor += n_ticks;
+  }
+  CK(rlm_launch_tick(h->ptr, d, h->cfg.n_envs, h->hp.env_stride, h->warps, h->stream));
+  h->launches++;
+  return RLM_OK;
+}
+
+int rlm_sync(rlm_handle h) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  unsigned long long c[8];
+  CK(cudaMemcpy(c, h->ptr.counters, sizeof(c), cudaMemcpyDeviceToHost));
+  unsigned err = (unsigned)c[4];
+  if (err) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "device error flags 0x%x:%s%s%s%s%s", err,
+             (err & ERR_BAD_PRICE) ? " non-positive price/volume (book.cpp:74-77)" : "",
+             (err & ERR_TICK_RANGE) ? " invalid price/ticks for conversion (market.cpp:86,112)" : "",
+             (err & ERR_TRACE_OVERFLOW) ? " trace list overflow (raise trace_cap)" : "",
+             (err & ERR_INVALID_STATE) ? " invalid book state (book.cpp:612-625)" : "",
+             (err & ERR_STREAM_UNDERRUN) ? " stream underrun" : "");
+    return fail((err & ERR_TICK_RANGE) ? RLM_ERR_INVALID_ARGUMENT : RLM_ERR_RUNTIME, buf);
+  }
+  return RLM_OK;
+}
+
+int rlm_get_counters(rlm_handle h, rlm_counters* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  unsigned long long c[8];
+  CK(cudaMemcpy(c, h->ptr.counters, sizeof(c), cudaMemcpyDeviceToHost));
+  out->ticks = (int64_t)c[0]; out->steps = (int64_t)c[1]; out->sum_traces = (int64_t)c[2];
+  out->terminal_envs = (int64_t)c[3]; out->kernel_launches = h->launches;
+  return RLM_OK;
+}
+
+static int fetch_hdrs(rlm_handle h, int env0, int n, std::vector<EnvHdr>& out) {
+  if (env0 < 0 || n < 0 || env0 + n > h->cfg.n_envs) return fail(RLM_ERR_INVALID_ARGUMENT, "env range out of bounds");
+  out.resize(n);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (n) CK(cudaMemcpy2D(out.data(), sizeof(EnvHdr), h->ptr.env + (size_t)env0 * h->hp.env_stride, h->hp.env_stride, sizeof(EnvHdr), n,
+                         cudaMemcpyDeviceToHost));
+  return RLM_OK;
+}
+
+int rlm_get_stats(rlm_handle h, int32_t env0, int32_t n, rlm_env_stats* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<EnvHdr> v;
+  int rc = fetch_hdrs(h, env0, n, v);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const EnvHdr& e = v[i];
+    rlm_env_stats& s = out[i];
+    s.episode_reward = e.ep_reward; s.episode_pnl = e.ep_pnl; s.episode_bandh = e.ep_bandh;
+    s.position = e.position;
+    s.ask_transactions = e.side[0].n_transacted; s.bid_transactions = e.side[1].n_transacted;
+    s.market_buys = e.market_buys; s.market_sells = e.market_sells;
+    s.total_ticks = e.ts_total; s.steps = e.ep_step;
+    s.terminal = e.phase == PH_DONE; s.phase = e.phase;
+  }
+  return RLM_OK;
+}
+
+int rlm_get_state(rlm_handle h, float* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<EnvHdr> v;
+  int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
+  if (rc) return rc;
+  for (int i = 0; i < h->cfg.n_envs; ++i)
+    for (int k = 0; k < h->cfg.n_state_vars; ++k) out[(size_t)i * h->cfg.n_state_vars + k] = v[i].from_vars[k];
+  return RLM_OK;
+}
+int rlm_get_reward(rlm_handle h, double* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<EnvHdr> v;
+  int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
+  if (rc) return rc;
+  for (int i = 0; i < h->cfg.n_envs; ++i) out[i] = v[i].last_reward;
+  return RLM_OK;
+}
+int rlm_get_actions(rlm_handle h, int32_t* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<EnvHdr> v;
+  int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
+  if (rc) return rc;
+  for (int i = 0; i < h->cfg.n_envs; ++i) out[i] = v[i].last_action;
+  return RLM_OK;
+}
+
+int rlm_handle_terminal(rlm_handle h, int32_t episode) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = upload_params(h);
+  if (rc) return rc;
+  CK(rlm_launch_clear_traces(h->ptr, h->cfg.n_envs, h->stream));  // traces.decay(0.0), agent.cpp:105
+  const rlm_config& c = h->cfg;
+  h->alpha = std::max(c.alpha_floor, c.alpha_start * pow(c.omega, (double)episode));  // agent.cpp:106
+  if (c.policy_type == RLM_POLICY_EPSILON_GREEDY) {                                   // policy.cpp:79-82
+    double e0 = (double)c.eps_init, ef = (double)c.eps_floor;
+    h->eps = e0 * pow(ef / e0, (double)episode / (double)(long)c.eps_T);
+  }
+  return RLM_OK;
+}
+
+int rlm_go_greedy(rlm_handle h) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  h->dyn.greedy = 1;  // Agent::GoGreedy, agent.cpp:76-79
+  return RLM_OK;
+}
+
+int rlm_read_theta(rlm_handle h, int32_t policy, int32_t table, double* out, int64_t n) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  if (policy < 0 || policy >= h->n_policies || n < 0 || n > h->cfg.memory_size) return fail(RLM_ERR_INVALID_ARGUMENT, "bad policy index / length");
+  double* src = table == 0 ? h->ptr.theta : h->ptr.theta_b;
+  if (!src) return fail(RLM_ERR_INVALID_ARGUMENT, "no such table");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, src + (size_t)policy * h->cfg.memory_size, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return RLM_OK;
+}
+int rlm_write_theta(rlm_handle h, int32_t policy, int32_t table, const double* in, int64_t n) {
+  if (!h || !in) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  if (policy < 0 || policy >= h->n_policies || n < 0 || n > h->cfg.memory_size) return fail(RLM_ERR_INVALID_ARGUMENT, "bad policy index / length");
+  double* dst = table == 0 ? h->ptr.theta : h->ptr.theta_b;
+  if (!dst) return fail(RLM_ERR_INVALID_ARGUMENT, "no such table");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(dst + (size_t)policy * h->cfg.memory_size, in, (size_t)n * 8, cudaMemcpyHostToDevice));
+  return RLM_OK;
+}
+
+int rlm_read_records(rlm_handle h, int32_t env, rlm_step_record* out, int32_t cap, int32_t* n_out) {
+  if (!h || !out || !n_out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  if (env < 0 || env >= h->hp.record_envs) return fail(RLM_ERR_INVALID_ARGUMENT, "env is not recorded (cfg.record_envs)");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  int cnt = 0;
+  CK(cudaMemcpy(&cnt, h->ptr.record_count + env, 4, cudaMemcpyDeviceToHost));
+  int n = std::min(std::min(cnt, h->hp.record_cap), cap);
+  if (n > 0) CK(cudaMemcpy(out, h->ptr.records + (size_t)env * h->hp.record_cap, (size_t)n * sizeof(rlm_step_record), cudaMemcpyDeviceToHost));
+  *n_out = n;
+  return RLM_OK;
+}
+
+int rlm_device_ptrs(rlm_handle h, void** theta, void** dtheta, int64_t* n_doubles) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  if (theta) *theta = h->ptr.theta;
+  if (dtheta) *dtheta = h->ptr.dtheta;
+  if (n_doubles) *n_doubles = (int64_t)h->n_policies * h->cfg.memory_size;
+  return RLM_OK;
+}
+int rlm_apply_dtheta(rlm_handle h) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  return fail(RLM_ERR_UNSUPPORTED, "shared_policy is not built yet in this round");
+}
+
+int rlm_flow_generate(const rlm_flow_params* p, int64_t env_index, int64_t first_tick, int32_t n_ticks, rlm_tick_msg* out) {
+  if (!p || !out || n_ticks < 0 || first_tick < 0) return fail(RLM_ERR_INVALID_ARGUMENT, "bad arguments");
+  rlm_flow_state s;
+  rlm_flow_init(&s, p, (uint64_t)env_index);
+  rlm_tick_msg tmp;
+  for (int64_t t = 0; t < first_tick; ++t) rlm_flow_next(&s, p, rlm_flow_skellam20_lut, rlm_flow_pois30_lut, rlm_flow_pois1p5_lut, &tmp);
+  for (int32_t t = 0; t < n_ticks; ++t) rlm_flow_next(&s, p, rlm_flow_skellam20_lut, rlm_flow_pois30_lut, rlm_flow_pois1p5_lut, &out[t]);
+  return RLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// unit-level device entry points
+static int test_setup(const rlm_config* cfg, rlm_handle_s& tmp) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RLM_ERR_NO_DEVICE, "no CUDA device (no CPU fallback)");
+  tmp.cfg = *cfg;
+  if (tmp.cfg.n_envs <= 0) tmp.cfg.n_envs = 1;
+  int rc = derive(&tmp);
+  if (rc) return rc;
+  CK(cudaSetDevice(cfg->device));
+  g_params_owner = nullptr;
+  CK(rlm_upload_params(&tmp.hp));
+  return RLM_OK;
+}
+
+int rlm_test_to_ticks(const rlm_config* cfg, const double* px, int32_t n, int32_t* out) {
+  rlm_handle_s tmp;
+  int rc = test_setup(cfg, tmp);
+  if (rc) return rc;
+  double* d_in; int* d_out;
+  CK(cudaMalloc(&d_in, n * 8)); CK(cudaMalloc(&d_out, n * 4));
+  CK(cudaMemcpy(d_in, px, n * 8, cudaMemcpyHostToDevice));
+  CK(rlm_launch_test_to_ticks(d_in, n, d_out));
+  CK(cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out);
+  return RLM_OK;
+}
+int rlm_test_to_price(const rlm_config* cfg, const int32_t* ticks, int32_t n, double* out) {
+  rlm_handle_s tmp;
+  int rc = test_setup(cfg, tmp);
+  if (rc) return rc;
+  int* d_in; double* d_out;
+  CK(cudaMalloc(&d_in, n * 4)); CK(cudaMalloc(&d_out, n * 8));
+  CK(cudaMemcpy(d_in, ticks, n * 4, cudaMemcpyHostToDevice));
+  CK(rlm_launch_test_to_price(d_in, n, d_out));
+  CK(cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out);
+  return RLM_OK;
+}
+int rlm_test_tiles(const rlm_config* cfg, const float* vars, int32_t n, int32_t* out) {
+  rlm_handle_s tmp;
+  int rc = test_setup(cfg, tmp);
+  if (rc) return rc;
+  float* d_in; int* d_out;
+  size_t nin = (size_t)n * cfg->n_state_vars, nout = (size_t)n * cfg->n_actions * 96;
+  CK(cudaMalloc(&d_in, nin * 4)); CK(cudaMalloc(&d_out, nout * 4));
+  CK(cudaMemcpy(d_in, vars, nin * 4, cudaMemcpyHostToDevice));
+  CK(rlm_launch_test_tiles(d_in, n, d_out));
+  CK(cudaMemcpy(out, d_out, nout * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out);
+  return RLM_OK;
+}
+int rlm_test_order(int64_t size, int64_t q_head, const rlm_order_op* ops, int32_t n_ops, rlm_order_state* out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RLM_ERR_NO_DEVICE, "no CUDA device (no CPU fallback)");
+  if (size <= 0) return fail(RLM_ERR_RUNTIME, "Order size must be non-zero and positive.");  // order.cpp:24-25
+  if (q_head < 0) return fail(RLM_ERR_RUNTIME, "Order queue must be positive.");             // order.cpp:26-27
+  for (int i = 0; i < n_ops; ++i)
+    if ((ops[i].op == 0 || ops[i].op == 1) && ops[i].arg < 0)
+      return fail(RLM_ERR_RUNTIME, ops[i].op == 0 ? "Transaction volume must be positive." : "Cancellation volume must be positive.");  // order.cpp:56-57,86-87
+  rlm_order_op* d_ops; rlm_order_state* d_out;
+  CK(cudaMalloc(&d_ops, n_ops * sizeof(rlm_order_op))); CK(cudaMalloc(&d_out, n_ops * sizeof(rlm_order_state)));
+  CK(cudaMemcpy(d_ops, ops, n_ops * sizeof(rlm_order_op), cudaMemcpyHostToDevice));
+  CK(rlm_launch_test_order(size, q_head, d_ops, n_ops, d_out));
+  CK(cudaMemcpy(out, d_out, n_ops * sizeof(rlm_order_state), cudaMemcpyDeviceToHost));
+  cudaFree(d_ops); cudaFree(d_out);
+  return RLM_OK;
+}
+int rlm_test_rolling_mean(int32_t window, const double* vals, int32_t n, double* out) {
+  rlm_config cfg;
+  rlm_config_default(&cfg);
+  cfg.memory_size = 1024; cfg.algorithm = RLM_ALGO_Q_LEARN;
+  cfg.lb_mpm = window;
+  rlm_handle_s tmp;
+  int rc = test_setup(&cfg, tmp);
+  if (rc) return rc;
+  double *d_in, *d_out, *d_ring; EnvHdr* d_e;
+  CK(cudaMalloc(&d_in, n * 8)); CK(cudaMalloc(&d_out, n * 16)); CK(cudaMalloc(&d_ring, (size_t)tmp.hp.ring_total * 8)); CK(cudaMalloc(&d_e, sizeof(EnvHdr)));
+  CK(cudaMemset(d_ring, 0, (size_t)tmp.hp.ring_total * 8)); CK(cudaMemset(d_e, 0, sizeof(EnvHdr)));
+  CK(cudaMemcpy(d_in, vals, n * 8, cudaMemcpyHostToDevice));
+  CK(rlm_launch_test_rolling_mean(d_in, n, d_out, d_ring, d_e));
+  CK(cudaMemcpy(out, d_out, n * 16, cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_ring); cudaFree(d_e);
+  return RLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,17 @@
+// rlm_kernels.h -- launch wrappers implemented in rlm_kernels.cu (host-callable).
+#pragma once
+#include <cuda_runtime.h>
+#include "rlm_types.h"
+
+size_t rlm_smem_bytes(int warps_per_cta, int env_stride);
+cudaError_t rlm_upload_params(const DevParams* p);
+cudaError_t rlm_launch_tick(const DevPtrs& ptr, const DynParams& D, int n_envs, int env_stride, int warps, cudaStream_t st);
+cudaError_t rlm_launch_init(const DevPtrs& ptr, int n_envs, int mode, cudaStream_t st);
+cudaError_t rlm_launch_seed(const DevPtrs& ptr, int n_envs, unsigned seed, cudaStream_t st);
+cudaError_t rlm_launch_random_init(const DevPtrs& ptr, int n_policies, cudaStream_t st);
+cudaError_t rlm_launch_clear_traces(const DevPtrs& ptr, int n_envs, cudaStream_t st);
+cudaError_t rlm_launch_test_to_ticks(const double* px, int n, int* out);
+cudaError_t rlm_launch_test_to_price(const int* t, int n, double* out);
+cudaError_t rlm_launch_test_tiles(const float* vars, int n, int* out);
+cudaError_t rlm_launch_test_order(long long size, long long q_head, const rlm_order_op* ops, int n_ops, rlm_order_state* out);
+cudaError_t rlm_launch_test_rolling_mean(const double* vals, int n, double* out, double* ring_mem, EnvHdr* e);

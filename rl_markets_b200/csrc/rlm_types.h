@@ -1,0 +1,126 @@
+// rlm_types.h -- device-side data layout of the batched LOB environment + agent.
+//
+// One `EnvHdr` (+ its window rings) per environment, array-of-structs in HBM:
+// a warp owns one env for a whole launch, stages the record into shared memory
+// with coalesced 16-byte loads, runs `n_ticks` market ticks on it and writes it
+// back, so the env record costs 2*S bytes of HBM traffic per LAUNCH, not per
+// tick.  The big per-env arrays (theta, the compact trace list, the Mersenne
+// Twister state) stay in HBM and are touched sparsely.
+#pragma once
+#include <stdint.h>
+#include "rlm.h"
+
+#define RLM_NWIN 10
+enum { W_MID = 0, W_VLT, W_VNUM, W_VDEN, W_SPREAD, W_TP, W_ASKTX, W_BIDTX, W_PNLUP, W_PNLDN };
+
+enum { PH_PREOPEN = 0, PH_WARMUP = 1, PH_RUN = 2, PH_DONE = 3 };
+
+// error bits accumulated per env (reported by rlm_sync as RLM_ERR_RUNTIME / INVALID_ARGUMENT)
+enum {
+  ERR_BAD_PRICE = 1,       // book.cpp:74-77 / order.cpp:22 (non-positive price or volume)
+  ERR_TICK_RANGE = 2,      // market.cpp:86,112 invalid price / tick for conversion
+  ERR_TRACE_OVERFLOW = 4,  // more nonzero traces than trace_cap (traces.h:13 MAX_NONZERO_TRACES analogue)
+  ERR_INVALID_STATE = 8,   // BookUtils::IsValidState false (the reference would merge rows)
+  ERR_STREAM_UNDERRUN = 16
+};
+
+struct OrderD {  // market::Order (include/market/order.h:11-51); one per side (ORDER_LIMIT == 1, base.cpp:21)
+  double price;
+  long long size, q_head, q_tail, executed, initial_queue;
+  int live;
+  int transactions;
+};
+
+struct SideD {  // market::Book<C,5> (include/market/book.h:22-110)
+  double px[RLM_DEPTH];
+  double last_px[RLM_DEPTH];
+  int vol[RLM_DEPTH];
+  int last_vol[RLM_DEPTH];
+  long long total_vol, last_total_vol;
+  double obs_value;
+  long long obs_volume;
+  int n_transacted;
+  int has_cur, has_last;  // levels / last_levels non-empty
+  int pad;
+  OrderD ord;
+};
+
+struct EnvHdr {
+  SideD side[2];  // 0 = ask, 1 = bid
+  long long position;  // RiskManager::position_
+  double pnl_step, momentum_pnl_step, ask_quote, bid_quote;  // Base members (base.h:55-63)
+  double agg_r, agg_pnl, agg_mpm;                            // locals of performAction kept across ticks
+  double tp_val, ewma_up, ewma_dn;
+  double ep_reward, ep_pnl, ep_bandh;
+  double last_reward, last_delta;
+  double q_from[RLM_MAX_ACTIONS];   // Q_A(from, .) under the current theta
+  double qb_from[RLM_MAX_ACTIONS];  // Q_B(from, .) (double agents)
+  double w_sum[RLM_NWIN], w_mean[RLM_NWIN], w_s[RLM_NWIN];
+  long long n_steps, n_ticks, sum_traces;
+  int w_head[RLM_NWIN], w_count[RLM_NWIN];
+  float from_vars[RLM_N_STATE_MAX + 3];  // state variables of the from-state
+  int phase, last_action, lo_vol_step, cur_action;
+  int ask_level, bid_level, date, last_date, time_ms;
+  int null_from;  // from-state is the never-populated State of serial.cpp:14-15,55 (all features 0)
+  int market_buys, market_sells;
+  int ts_total, ts_ask, ts_bid, ts_both, ts_pos, ts_long, ts_short;
+  int ep_step, n_traces, err, stream_pos;
+  int mt_pol_idx, mt_agt_idx;  // std::mt19937_64::_M_p
+  int crand_f, crand_b;
+  int crand_r[31];
+  int pad0;
+  rlm_flow_state flow;
+  int pad1;
+};
+
+struct VenueD {
+  int n;
+  int cum_full[RLM_MAX_BANDS];   // ticks after fully traversing bands 0..k-1 (market.cpp:88-99 chain)
+  int tts_tick[RLM_MAX_BANDS];   // Market::tts_ keys (market.cpp:27-37)
+  double px[RLM_MAX_BANDS], ts[RLM_MAX_BANDS];
+  double cum_price[RLM_MAX_BANDS];  // price after fully traversing tts_ bands 0..k-1 (market.cpp:115-125 chain)
+  long long open_lo, close_hi;      // IsOpen bounds: mo+30min, mc-30min (market.cpp:67-70)
+};
+
+struct DevParams {
+  int n_envs, n_actions, algorithm, policy_type, reward_measure, n_state_vars;
+  int state_vars[RLM_N_STATE_MAX];
+  int tp_is_micro, l2p_book, order_size, source, shared_policy, is_double;
+  long long pos_lb, pos_ub, memory_size;
+  unsigned long long m_magic;  // floor(2^64 / M)
+  int m_pow2;
+  float gl;  // (float)(gamma*lambda): Traces::decay(float rate)
+  double gw[3], gamma;
+  float damping, pos_weight, trd_weight, pnl_weight;
+  double ewma_alpha;
+  int win_size[RLM_NWIN], win_off[RLM_NWIN];
+  int ring_total;       // doubles per env
+  int env_stride;       // bytes per env record in HBM (multiple of 16)
+  int trace_cap, record_envs, record_cap;
+  long long env_index0;
+  VenueD venue;
+  rlm_flow_params flow;
+};
+
+struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
+  double alpha, eps;
+  int greedy;
+  int n_ticks;
+  int stream_ticks;   // ticks in the resident stream chunk
+  int stream_off;     // first tick of the chunk this launch consumes
+};
+
+struct DevPtrs {
+  unsigned char* env;       // [n_envs][env_stride]
+  double* theta;            // [n_policies][M]
+  double* theta_b;          // [n_policies][M] or null
+  double* dtheta;           // shared policy: accumulated delta, [M]
+  int* trace_f;             // [n_envs][trace_cap]
+  float* trace_e;           // [n_envs][trace_cap]
+  unsigned long long* mt_pol;  // [n_envs][312]
+  unsigned long long* mt_agt;  // [n_envs][312] or null
+  const rlm_tick_msg* stream;  // [stream_ticks][n_envs]
+  rlm_step_record* records;    // [record_envs][record_cap]
+  int* record_count;           // [record_envs]
+  unsigned long long* counters;  // [8]: ticks, steps, sum_traces, terminal, err
+};
