@@ -1287,6 +1287,7 @@ void lobo_book_script(const lobo_book_op* ops, int32_t n_ops, lobo_book_result* 
   Side ask, bid;
   ask.is_ask = true; bid.is_ask = false;
   ask.Reset(); bid.Reset();
+  Tx pending;  // op 6 sets the prints handed to the following ApplyChanges calls (book.cpp:67,94-95)
   for (int i = 0; i < n_ops; ++i) {
     const lobo_book_op& op = ops[i];
     Side& s = op.side == 0 ? ask : bid;
@@ -1297,11 +1298,10 @@ void lobo_book_script(const lobo_book_op* ops, int32_t n_ops, lobo_book_result* 
       switch (op.op) {
         case 0: {
           s.depth = op.n;
-          Tx none;
           long v[RLM_DEPTH];
           for (int l = 0; l < op.n; ++l) v[l] = op.vol[l];
           s.StashState();
-          s.ApplyChanges(op.px, v, none);
+          s.ApplyChanges(op.px, v, pending);
           break;
         }
         case 1: r.r_ok = s.PlaceOrder(op.a, op.b) ? 1 : 0; break;
@@ -1314,6 +1314,7 @@ void lobo_book_script(const lobo_book_op* ops, int32_t n_ops, lobo_book_result* 
         case 3: { long v; adverse_selection(ask, bid, v, r.r_proxy, r.r_value); r.r_volume = v; break; }
         case 4: { long v; s.WalkTheBook(op.a, op.b, v, r.r_proxy, r.r_value); r.r_volume = v; break; }
         case 5: s.CancelAll(); break;
+        case 6: pending.n = op.n; for (int k = 0; k < op.n; ++k) { pending.px[k] = op.px[k]; pending.vol[k] = op.vol[k]; } break;
       }
     } catch (const std::exception&) { r.r_ok = -1; }
     r.n_transacted = s.n_transacted_;

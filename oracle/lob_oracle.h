@@ -65,7 +65,8 @@ uint32_t lobo_uniform_int(uint64_t seed, uint32_t n, int32_t n_skip);
 /* Book scenario replay (test/test_Book.cpp): a tiny interpreter, see tests/test_golden_book.py */
 typedef struct lobo_book_op {
   int32_t op;      /* 0 ApplyChanges(prices,vols)+Stash  1 PlaceOrder(side,price,size)  2 ApplyTransactions(side,ref)
-                      3 AdverseSelection  4 WalkTheBook(side,ref,size)  5 CancelAll(side) */
+                      3 AdverseSelection  4 WalkTheBook(side,ref,size)  5 CancelAll(side)
+                      6 set the prints (px,vol,n) handed to the following ApplyChanges calls */
   int32_t side;    /* 0 ask, 1 bid */
   double px[5];    /* op0: prices of `side`; op2: tx prices */
   int64_t vol[5];  /* op0: volumes; op2: tx volumes */

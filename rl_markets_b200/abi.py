@@ -1,8 +1,8 @@
 """ctypes mirror of include/rlm.h, include/rlm_flow.h and include/rlm_record.h.
 
-Plain-C structures only; nothing here touches torch.  The same structures are
-used to talk to the product library (rl_markets_b200/csrc -> librlm.so) and, in
-tests / bench baselines only, to the CPU oracle (oracle/liblob_oracle.so).
+Plain-C structures only; nothing here touches torch.  These are the structures of the
+product library (rl_markets_b200/csrc -> librlm.so); the test-side checker speaks the same
+C structs but is never imported from here.
 """
 import ctypes as C
 

@@ -12,14 +12,13 @@
 #include "rlm_env.cuh"
 
 #define FULL 0xffffffffu
-#define HS_SLOTS 512
 #define HS_EMPTY (-1)
 
 // ------------------------------------------------------------------ RNGs (lane 0)
 // std::mt19937_64, regenerated one word at a time: equivalent to the batch twist of
 // libstdc++'s _M_gen_rand because word k only depends on old x[k], old-or-new x[k+1] and
 // x[k+156 mod 312] exactly as they stand when the batch loop reaches k.
-__device__ unsigned long long mt_next(unsigned long long* x, int& p) {
+__device__ __noinline__ unsigned long long mt_next(unsigned long long* x, int& p) {
   int k = p; if (k >= 312) k -= 312;   // _M_p == 312 means "regenerate": start at word 0
   const unsigned long long UM = 0xFFFFFFFF80000000ull, LM = 0x7FFFFFFFull, A = 0xB5026F5AA96619E9ull;
   int k1 = k + 1; if (k1 == 312) k1 = 0;
@@ -35,13 +34,13 @@ __device__ unsigned long long mt_next(unsigned long long* x, int& p) {
   return z;
 }
 // generate_canonical<double,53> on a 64-bit URBG + uniform_real_distribution(0,1)
-__device__ double mt_uniform_real(unsigned long long* x, int& p) {
+__device__ __noinline__ double mt_uniform_real(unsigned long long* x, int& p) {
   double r = __ull2double_rn(mt_next(x, p)) / 18446744073709551616.0;
   if (r >= 1.0) r = 0.99999999999999988897769753748;  // nextafter(1,0)
   return r * (1.0 - 0.0) + 0.0;
 }
 // uniform_int_distribution<unsigned>(0,n-1): Lemire with a 128-bit product
-__device__ unsigned mt_uniform_int(unsigned long long* x, int& p, unsigned n) {
+__device__ __noinline__ unsigned mt_uniform_int(unsigned long long* x, int& p, unsigned n) {
   unsigned long long range = n;
   unsigned long long g = mt_next(x, p);
   unsigned long long low = g * range, hi = __umul64hi(g, range);
@@ -55,7 +54,7 @@ __device__ unsigned mt_uniform_int(unsigned long long* x, int& p, unsigned n) {
   return (unsigned)hi;
 }
 // glibc rand() (random_r TYPE_3)
-__device__ int crand_next(EnvHdr& e) {
+__device__ __noinline__ int crand_next(EnvHdr& e) {
   unsigned v = (unsigned)e.crand_r[e.crand_f] + (unsigned)e.crand_r[e.crand_b];
   e.crand_r[e.crand_f] = (int)v;
   int out = (int)(v >> 1);
@@ -66,7 +65,7 @@ __device__ int crand_next(EnvHdr& e) {
 
 // ------------------------------------------------------------------ windows (lane w = window w)
 // Accumulator<double>::push / RollingMean<double>::push (accumulators.cpp:17-27,86-109)
-__device__ __forceinline__ void window_push(EnvHdr& e, double* ring, int w, double val) {
+__device__ __noinline__ void window_push(EnvHdr& e, double* ring, int w, double val) {
   const int ws = P.win_size[w];
   double* r = ring + P.win_off[w];
   int head = e.w_head[w], cnt = e.w_count[w];
@@ -110,7 +109,7 @@ __device__ __forceinline__ int tile_coord(int q, int i, int j) {
 
 // Partial hash sum (everything except the action-dependent integer) for lane j's tiling of one
 // feature group: floats vars[0..nf) then the tiling index (tiles.cpp:65-68, hash_UNH :152-161).
-__device__ __forceinline__ unsigned long long tile_base_sum(const unsigned* rnd, const float* vars, int nf, int j) {
+__device__ __noinline__ unsigned long long tile_base_sum(const unsigned* rnd, const float* vars, int nf, int j) {
   unsigned long long sum = 0;
   for (int i = 0; i < nf; ++i) {
     int q = (int)floorf(vars[i] * (float)RLM_N_TILINGS);
@@ -130,17 +129,30 @@ __device__ __forceinline__ int tile_index(const unsigned* rnd, unsigned long lon
 // strictly left to right, so the result is bitwise the reference's.
 // vars: state variables (n of them) in shared memory; vbuf: >= 2*A*32 doubles of scratch.
 // If null_state, every feature index is 0 (the never-populated State of serial.cpp:14-15,55).
-__device__ void eval_q(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
-                       bool null_state, double* vbuf, int lane, double& qa_out, double& qb_out) {
+#define VROW 33  // padded row stride (doubles) of the transposition buffer: conflict-free for lanes 0..8
+__device__ __forceinline__ double seg_sum(double acc, double w, const double* r) {
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) acc += w * r[i];
+  return acc;
+}
+// bases[g]: lane j's partial hash sum of group g; computed when !reuse, reused otherwise (the two
+// evaluations of one learner step -- before and after the weight update -- are on the same state).
+__device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
+                       bool null_state, double* vbuf, int lane, double& qa_out, double& qb_out,
+                       unsigned long long* bases, bool reuse) {
   const int A = P.n_actions;
   double qa = 0.0, qb = 0.0;
   double* va = vbuf;
-  double* vb = vbuf + RLM_MAX_ACTIONS * 32;
+  double* vb = vbuf + RLM_MAX_ACTIONS * VROW;
 #pragma unroll 1
   for (int g = 0; g < 3; ++g) {
     const float* gv = (g == 1) ? vars + 3 : vars;
     const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
-    unsigned long long base = null_state ? 0ull : tile_base_sum(rnd, gv, nf, lane);
+    unsigned long long base = 0ull;
+    if (!null_state) {
+      if (reuse) base = bases[g];
+      else { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
+    }
     double ta[RLM_MAX_ACTIONS], tb[RLM_MAX_ACTIONS];
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
@@ -153,29 +165,21 @@ __device__ void eval_q(const unsigned* rnd, const double* th_a, const double* th
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
       if (a < A) {
-        va[a * 32 + lane] = ta[a];
-        if (th_b) vb[a * 32 + lane] = tb[a];
+        va[a * VROW + lane] = ta[a];
+        if (th_b) vb[a * VROW + lane] = tb[a];
       }
     }
     __syncwarp();
     if (lane < A) {
-      const double* ra = va + lane * 32;
-      const double* rb = vb + lane * 32;
-      if (g == 0) {
-        const double w = P.gw[0];
-        for (int i = 0; i < 32; ++i) qa += w * ra[i];
-        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
-      } else if (g == 1) {
-        double w = P.gw[1];
-        for (int i = 0; i < 32; ++i) qa += w * ra[i];
-        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
-        w = P.gw[2];  // the third loop starts at T, not 2T
-        for (int i = 0; i < 32; ++i) qa += w * ra[i];
-        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
-      } else {
-        const double w = P.gw[2];
-        for (int i = 0; i < 32; ++i) qa += w * ra[i];
-        if (th_b) for (int i = 0; i < 32; ++i) qb += w * rb[i];
+      const double* ra = va + lane * VROW;
+      const double* rb = vb + lane * VROW;
+      // g=0: w0 | g=1: w1 then w2 (the third loop starts at T, not 2T: SURVEY Appendix A8) | g=2: w2
+      const int npass = (g == 1) ? 2 : 1;
+#pragma unroll 1
+      for (int pass = 0; pass < npass; ++pass) {
+        const double w = P.gw[(g == 0) ? 0 : ((g == 1) ? 1 + pass : 2)];
+        qa = seg_sum(qa, w, ra);
+        if (th_b) qb = seg_sum(qb, w, rb);
       }
     }
     __syncwarp();
@@ -185,7 +189,7 @@ __device__ void eval_q(const unsigned* rnd, const double* th_a, const double* th
 }
 
 // argmax with rand() tie-breaks over q[0..A) (agent.cpp:144-169); lane 0
-__device__ int argmax_ties(EnvHdr& e, const double* q) {
+__device__ __noinline__ int argmax_ties(EnvHdr& e, const double* q) {
   int index = 0, n_ties = 1;
   double cur = q[0];
   for (int a = 1; a < P.n_actions; a++) {
@@ -201,7 +205,7 @@ __device__ int argmax_ties(EnvHdr& e, const double* q) {
   return index;
 }
 // Greedy::Sample (policy.cpp:37-55); lane 0
-__device__ int greedy_sample(EnvHdr& e, const double* qs) {
+__device__ __noinline__ int greedy_sample(EnvHdr& e, const double* qs) {
   int argmax = 0, n_ties = 1;
   for (int a = 1; a < P.n_actions; a++) {
     if (qs[a] > qs[argmax]) argmax = a;
@@ -213,7 +217,7 @@ __device__ int greedy_sample(EnvHdr& e, const double* qs) {
   return argmax;
 }
 // Agent::action / DoubleAgent::action + Policy::Sample; lane 0.  qa/qb: Q_A(s,.), Q_B(s,.)
-__device__ int policy_action(EnvHdr& e, const double* qa, const double* qb, unsigned long long* mt, const DynParams& D) {
+__device__ __noinline__ int policy_action(EnvHdr& e, const double* qa, const double* qb, unsigned long long* mt, const DynParams& D) {
   double qs[RLM_MAX_ACTIONS];
   for (int a = 0; a < P.n_actions; ++a) qs[a] = P.is_double ? (qa[a] + qb[a]) / 2.0 : qa[a];
   int pt = D.greedy ? RLM_POLICY_GREEDY : P.policy_type;
@@ -231,54 +235,63 @@ __device__ int policy_action(EnvHdr& e, const double* qa, const double* qb, unsi
 //   Traces::update(from, action)   for a = 0..A-1: clear / set the 32 group-0 tiles   traces.cpp:40-50
 //   Agent::updateQ(alpha*delta)    theta[f] += (alpha*delta/32) * e[f]                agent.cpp:137-142
 // update()'s outcome for a feature f touched by it is decided by the LAST action whose tile list
-// contains f (set if that action is the one taken, cleared otherwise); a small open-addressed
-// hash set in shared memory maps f -> last such action.
-__device__ __forceinline__ unsigned hs_hash(int f) { return ((unsigned)f * 2654435761u) >> 23; }  // 9 bits
-
-__device__ int trace_pass(EnvHdr& e, const unsigned* rnd, int* hs_keys, int* hs_vals, int* tf, float* te,
-                          double* theta, int action, float rate, double scaled_update, int lane) {
+// contains f (set if that action is the one taken, cleared otherwise).  Tile (j, a) of the
+// from-state is (b_j + r_a) mod M with b_j = lane j's partial hash sum mod M (EnvHdr::from_base0)
+// and r_a = rndseq[(a + 449*4) & 2047] mod M (DevParams::ra_m), so "f is a tile of action a" is
+// "(f - r_a) mod M is one of the 32 b_j": a 64-slot hash set of the b_j answers it with A probes.
+#define SS_SLOTS 64
+__device__ __forceinline__ unsigned ss_hash(int x) { return ((unsigned)x * 2654435761u) >> 26; }  // 6 bits
+__device__ __forceinline__ bool ss_member(const int* ss, int x) {
+  unsigned slot = ss_hash(x);
+  while (true) {
+    int k = ss[slot];
+    if (k == x) return true;
+    if (k == HS_EMPTY) return false;
+    slot = (slot + 1) & (SS_SLOTS - 1);
+  }
+}
+// last action whose group-0 tile list contains f, or -1
+__device__ __forceinline__ int last_writer(const int* ss, int f, bool null_from) {
   const int A = P.n_actions;
-  // group-0 tiles of the from-state for every action (state.cpp:55-57)
-  int F[RLM_MAX_ACTIONS];
-  {
-    unsigned long long base = e.null_from ? 0ull : tile_base_sum(rnd, e.from_vars, 3, lane);
-#pragma unroll
-    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) F[a] = (a < A) ? (e.null_from ? 0 : tile_index(rnd, base, 3, a)) : 0;
+  if (null_from) return f == 0 ? A - 1 : -1;  // every tile of every action is feature 0
+  int la = -1;
+#pragma unroll 1
+  for (int a = 0; a < A; ++a) {
+    int x = f - P.ra_m[a];
+    if (x < 0) x += (int)P.memory_size;
+    if (ss_member(ss, x)) la = a;
   }
-  for (int i = lane; i < HS_SLOTS; i += 32) { hs_keys[i] = HS_EMPTY; hs_vals[i] = -1; }
+  return la;
+}
+
+__device__ __noinline__ int trace_pass(EnvHdr& e, int* ss, int* tf, float* te, double* theta, int action, float rate,
+                                       double scaled_update, int lane) {
+  const bool null_from = e.null_from != 0;
+  const int b0 = e.from_base0[lane];
+  ss[lane] = HS_EMPTY; ss[lane + 32] = HS_EMPTY;
   __syncwarp();
-#pragma unroll
-  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
-    if (a < A) {
-      unsigned slot = hs_hash(F[a]);
-      while (true) {
-        int old = atomicCAS(&hs_keys[slot], HS_EMPTY, F[a]);
-        if (old == HS_EMPTY || old == F[a]) { atomicMax(&hs_vals[slot], a); break; }
-        slot = (slot + 1) & (HS_SLOTS - 1);
-      }
-    }
-  }
-  __syncwarp();
-  auto lookup = [&](int f) -> int {  // last action touching f, or -1
-    unsigned slot = hs_hash(f);
+  if (!null_from) {
+    unsigned slot = ss_hash(b0);
     while (true) {
-      int k = hs_keys[slot];
-      if (k == f) return hs_vals[slot];
-      if (k == HS_EMPTY) return -1;
-      slot = (slot + 1) & (HS_SLOTS - 1);
+      int old = atomicCAS(&ss[slot], HS_EMPTY, b0);
+      if (old == HS_EMPTY || old == b0) break;
+      slot = (slot + 1) & (SS_SLOTS - 1);
     }
-  };
+  }
+  __syncwarp();
   const float tol = 0.01f;
   int w = 0;
   if (rate != 0.0f) {
     const int n = e.n_traces;
+#pragma unroll 1
     for (int base = 0; base < n; base += 32) {
       int i = base + lane;
       bool valid = i < n;
       int f = valid ? tf[i] : 0;
       float ev = valid ? te[i] : 0.0f;
       ev *= rate;
-      bool keep = valid && !(ev < tol) && (lookup(f) < 0);
+      bool keep = valid && !(ev < tol);
+      if (keep) keep = last_writer(ss, f, null_from) < 0;
       unsigned mask = __ballot_sync(FULL, keep);
       int pos = w + __popc(mask & ((1u << lane) - 1u));
       if (keep) {
@@ -291,10 +304,12 @@ __device__ int trace_pass(EnvHdr& e, const unsigned* rnd, int* hs_keys, int* hs_
   }
   // set(): the taken action's tiles that no later action cleared; one entry per distinct f
   {
-    int f = F[0];
-#pragma unroll
-    for (int a = 1; a < RLM_MAX_ACTIONS; ++a) if (a == action) f = F[a];
-    bool add = (lookup(f) == action);
+    int f = 0;
+    if (!null_from) {
+      f = b0 + P.ra_m[action];
+      if (f >= (int)P.memory_size) f -= (int)P.memory_size;
+    }
+    bool add = (last_writer(ss, f, null_from) == action);
     unsigned same = __match_any_sync(FULL, f);
     add = add && ((__ffs(same) - 1) == lane);
     unsigned mask = __ballot_sync(FULL, add);
@@ -317,7 +332,7 @@ __device__ int trace_pass(EnvHdr& e, const unsigned* rnd, int* hs_keys, int* hs_
 }
 
 // order-independent hash of {(f, e, theta[f])} for the parity record
-__device__ unsigned long long trace_hash(const int* tf, const float* te, const double* theta, int n, int lane) {
+__device__ __noinline__ unsigned long long trace_hash(const int* tf, const float* te, const double* theta, int n, int lane) {
   unsigned long long h = 0;
   for (int i = lane; i < n; i += 32) {
     int f = tf[i];

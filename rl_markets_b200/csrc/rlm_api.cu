@@ -14,7 +14,10 @@
 
 #include "rlm.h"
 #include "rlm_flow_tables.h"
+#include "rlm_rndseq.h"
 #include "rlm_kernels.h"
+#include <limits.h>
+#include <stdlib.h>
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -111,6 +114,9 @@ static int derive(rlm_handle_s* h) {
   p.m_pow2 = ((c.memory_size & (c.memory_size - 1)) == 0) ? 1 : 0;
   p.m_magic = (unsigned long long)((((unsigned __int128)1) << 64) / (unsigned __int128)c.memory_size);
   if (c.memory_size == 1) p.m_magic = ~0ull;
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a)  // hash_UNH term of the action integer for feature group 0 (3 floats + tiling + int)
+    p.ra_m[a] = (int)((unsigned long long)rlm_rndseq_table[(a + 449 * 4) & 2047] % (unsigned long long)c.memory_size);
+  p.scratch_bytes = (int)rlm_scratch_bytes(p.is_double);
   p.gl = (float)(c.gamma * c.lambda);  // Traces::decay(float rate) narrows gamma*lambda (A11)
   for (int i = 0; i < 3; ++i) p.gw[i] = c.group_weights[i];
   p.gamma = c.gamma;
@@ -145,6 +151,7 @@ static int derive(rlm_handle_s* h) {
   // ---- venue chains (src/market/market.cpp:27-37, 78-128), same fp64 operation order as the reference
   VenueD& v = p.venue;
   v.n = c.n_bands;
+  for (int i = 0; i < RLM_MAX_BANDS; ++i) { v.px[i] = INFINITY; v.ts[i] = 1.0; v.tts_tick[i] = INT_MAX; }
   for (int i = 0; i < c.n_bands; ++i) {
     v.px[i] = c.band_px[i]; v.ts[i] = c.band_ts[i];
     if (i > 0 && !(c.band_px[i] > c.band_px[i - 1])) return fail(RLM_ERR_INVALID_ARGUMENT, "venue bands must ascend");
@@ -240,10 +247,14 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   {
     int dev_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-    while (h->warps > 4 && rlm_smem_bytes(h->warps, p.env_stride) > (size_t)dev_smem) h->warps = (h->warps == 14) ? 8 : 4;
-    if (rlm_smem_bytes(h->warps, p.env_stride) > (size_t)dev_smem)
+    while (h->warps > 4 && rlm_smem_bytes(h->warps, p.env_stride, p.scratch_bytes) > (size_t)dev_smem) h->warps = (h->warps == 14) ? 8 : 4;
+    if (rlm_smem_bytes(h->warps, p.env_stride, p.scratch_bytes) > (size_t)dev_smem)
       return fail(RLM_ERR_UNSUPPORTED, "window lookbacks too large for shared memory staging");
   }
+  // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  if (const char* s = getenv("RLM_TICK_SYNC")) h->dyn.tick_sync = atoi(s);
+  if (const char* s = getenv("RLM_WARPS")) { int w = atoi(s); if (w == 4 || w == 8 || w == 14 || w == 16) h->warps = w; }
   CK(cudaStreamSynchronize(h->stream));
   *out = h;
   return RLM_OK;
@@ -316,7 +327,7 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     d.stream_ticks = h->stream_ticks;
     h->stream_cursor += n_ticks;
   }
-  CK(rlm_launch_tick(h->ptr, d, h->cfg.n_envs, h->hp.env_stride, h->warps, h->stream));
+  CK(rlm_launch_tick(h->ptr, d, h->cfg.n_envs, h->hp.env_stride, h->hp.scratch_bytes, h->warps, h->stream));
   h->launches++;
   return RLM_OK;
 }

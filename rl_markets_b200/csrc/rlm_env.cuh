@@ -35,12 +35,12 @@ __device__ __forceinline__ long long d2ll_x86(double d) {
 // Market::ToTicks (market.cpp:78-102).  Bands below the one containing `price` contribute a
 // price-independent chain of truncating `int += double` steps, precomputed on the host
 // (VenueD::cum_full); the loop below is the reference loop entered at that band.
-__device__ int to_ticks(double price, int* err) {
+__device__ __noinline__ int to_ticks(double price, int* err) {
   const VenueD& V = P.venue;
   if (price < V.px[0]) { *err |= ERR_TICK_RANGE; return 0; }
-  int k = 0;
-#pragma unroll 1
-  while (k + 1 < V.n && !(price < V.px[k + 1])) ++k;
+  int k = 0;  // band containing price: number of band starts px[1..n) that are <= price
+#pragma unroll
+  for (int i = 1; i < RLM_MAX_BANDS; ++i) k += !(price < V.px[i]) ? 1 : 0;  // px[i >= n] = +inf
   int ticks = V.cum_full[k];
   double tsp = V.ts[k];  // tick_size(price) = band containing price (market.cpp:130-138)
   int it = k;
@@ -56,13 +56,13 @@ __device__ int to_ticks(double price, int* err) {
 }
 
 // Market::ToPrice (market.cpp:104-128), same prefix trick on Market::tts_.
-__device__ double to_price(int ticks, int* err) {
+__device__ __noinline__ double to_price(int ticks, int* err) {
   const VenueD& V = P.venue;
   if (ticks < V.tts_tick[0]) { *err |= ERR_TICK_RANGE; return 0.0; }
   if (!(ticks > V.tts_tick[0])) return 0.0;
   int k = 0;
-#pragma unroll 1
-  while (k + 1 < V.n && ticks >= V.tts_tick[k + 1]) ++k;
+#pragma unroll
+  for (int i = 1; i < RLM_MAX_BANDS; ++i) k += (ticks >= V.tts_tick[i]) ? 1 : 0;  // tts_tick[i >= n] = INT_MAX
   // bands 0..k-1 fully traversed; band k partially (or exactly to its end when ticks == next key)
   double price = V.cum_price[k];
   if (ticks > V.tts_tick[k]) price += ((double)ticks - (double)V.tts_tick[k]) * V.ts[k];
@@ -83,7 +83,7 @@ __device__ __forceinline__ long long ord_remaining(const OrderD& o) {  // order.
 }
 __device__ __forceinline__ bool ord_is_executed(const OrderD& o) { return o.executed >= o.size; }  // :49-52
 
-__device__ long long ord_do_transaction(OrderD& o, long long volume) {  // order.cpp:54-82
+__device__ __noinline__ long long ord_do_transaction(OrderD& o, long long volume) {  // order.cpp:54-82
   o.transactions += (int)volume;
   long long remaining_volume = volume - o.q_head;
   if (remaining_volume > 0) {
@@ -101,7 +101,7 @@ __device__ long long ord_do_transaction(OrderD& o, long long volume) {  // order
   return remaining_volume > 0 ? remaining_volume : 0;
 }
 
-__device__ void ord_do_cancellation(OrderD& o, long long volume) {  // order.cpp:84-107
+__device__ __noinline__ void ord_do_cancellation(OrderD& o, long long volume) {  // order.cpp:84-107
   if (o.q_tail == 0) {
     o.q_head -= volume;
   } else {
@@ -137,7 +137,7 @@ __device__ long long side_last_volume(const SideD& s, double price) {  // book.c
   return v;
 }
 
-__device__ void side_reset(SideD& s) {  // book.cpp:143-160
+__device__ __noinline__ void side_reset(SideD& s) {  // book.cpp:143-160
   s.n_transacted = 0; s.obs_value = 0.0; s.obs_volume = 0;
   s.total_vol = 0; s.last_total_vol = 0;
   for (int l = 0; l < RLM_DEPTH; ++l) { s.px[l] = 0.0; s.last_px[l] = 0.0; s.vol[l] = 0; s.last_vol[l] = 0; }
@@ -147,7 +147,7 @@ __device__ void side_reset(SideD& s) {  // book.cpp:143-160
 
 // Book::PlaceOrder (book.cpp:249-261) after RiskManager::PlaceOrder's CancelWorst
 // (risk_manager.cpp:61-99): with one order per side the old order is always replaced.
-__device__ void side_replace_order(SideD& s, double price, long long size, int* err) {
+__device__ __noinline__ void side_replace_order(SideD& s, double price, long long size, int* err) {
   if (price <= 0 || size <= 0) { *err |= ERR_BAD_PRICE; s.ord.live = 0; return; }  // order.cpp:22-27
   OrderD& o = s.ord;
   o.live = 1; o.price = price; o.size = size;
@@ -156,7 +156,7 @@ __device__ void side_replace_order(SideD& s, double price, long long size, int* 
 }
 
 // Book::UpdateOrder (book.cpp:101-141)
-__device__ void side_update_order(SideD& s, long long transaction_volume) {
+__device__ __noinline__ void side_update_order(SideD& s, long long transaction_volume) {
   OrderD& o = s.ord;
   if (!o.live) return;
   if (ord_is_executed(o)) { o.live = 0; return; }
@@ -175,7 +175,7 @@ __device__ void side_update_order(SideD& s, long long transaction_volume) {
 
 // Book::StashState + Book::ApplyChanges for one depth row (book.cpp:50-55,63-99).
 // px/vol: the side's 5 levels, best first (the stream contract; rlm_load_ticks validates order).
-__device__ void side_apply_changes(SideD& s, const float* px, const int* vol, const rlm_tick_msg& m, int* err) {
+__device__ __noinline__ void side_apply_changes(SideD& s, const float* px, const int* vol, const rlm_tick_msg& m, int* err) {
 #pragma unroll
   for (int l = 0; l < RLM_DEPTH; ++l) { s.last_px[l] = s.px[l]; s.last_vol[l] = s.vol[l]; }
   s.has_last = s.has_cur;
@@ -205,7 +205,7 @@ struct Fill { long long volume; double proxy, value; };
 
 // AskBook::ApplyTransactions (book.cpp:382-427) / BidBook::ApplyTransactions (:467-510)
 template <bool IS_ASK>
-__device__ Fill side_apply_transactions(SideD& s, const rlm_tick_msg& m, double ref, bool use_tx) {
+__device__ __noinline__ Fill side_apply_transactions(SideD& s, const rlm_tick_msg& m, double ref, bool use_tx) {
   s.obs_value = 0.0;
   s.obs_volume = 0;
   Fill f; f.volume = 0; f.proxy = 0.0; f.value = 0.0;
@@ -240,7 +240,7 @@ __device__ Fill side_apply_transactions(SideD& s, const rlm_tick_msg& m, double 
 
 // AskBook/BidBook::WalkTheBook (book.cpp:429-456,512-539)
 template <bool IS_ASK>
-__device__ Fill side_walk(SideD& s, double ref, long long size) {
+__device__ __noinline__ Fill side_walk(SideD& s, double ref, long long size) {
   Fill f; f.volume = 0; f.proxy = 0.0; f.value = 0.0;
   long long abs_size = size < 0 ? -size : size;
   if (abs_size > s.total_vol) return f;
@@ -272,7 +272,7 @@ __device__ __forceinline__ double m_microprice(const EnvHdr& e) {  // measures.h
 }
 
 // BookUtils::HandleAdverseSelection (book.cpp:550-592)
-__device__ Fill adverse_selection(EnvHdr& e) {
+__device__ __noinline__ Fill adverse_selection(EnvHdr& e) {
   SideD& ask = e.side[0];
   SideD& bid = e.side[1];
   const double bap = ask.px[0], bbp = bid.px[0], rp = m_last_midprice(e);
@@ -318,7 +318,7 @@ __device__ __forceinline__ double win_std(const EnvHdr& e, int w) {  // accumula
 }
 
 // Base::getReward (base.cpp:166-237)
-__device__ double get_reward(const EnvHdr& e) {
+__device__ __noinline__ double get_reward(const EnvHdr& e) {
   double r = 0.0;
   long long ap = e.position < 0 ? -e.position : e.position;
   int abs_pos = (int)ap;
@@ -352,7 +352,7 @@ __device__ double get_reward(const EnvHdr& e) {
 
 // Base::ClearInventory + RiskManager::ClearInventory/MarketOrder + BookUtils::MarketOrder
 // (base.cpp:339-349, risk_manager.cpp:101-113, book.cpp:594-610)
-__device__ void clear_inventory(EnvHdr& e) {
+__device__ __noinline__ void clear_inventory(EnvHdr& e) {
   long long size = -e.position;
   Fill f; f.volume = 0; f.proxy = 0.0; f.value = 0.0;
   double mip = m_midprice(e);
@@ -367,7 +367,7 @@ __device__ void clear_inventory(EnvHdr& e) {
 }
 
 // Intraday::l2p_ + _place_orders (intraday.cpp:64-82,163-173)
-__device__ void place_orders(EnvHdr& e, int al, int bl) {
+__device__ __noinline__ void place_orders(EnvHdr& e, int al, int bl) {
   e.ask_level = al; e.bid_level = bl;
   if (P.l2p_book) {
     e.ask_quote = to_price(to_ticks(e.side[0].px[0], &e.err) + al, &e.err);
@@ -381,23 +381,26 @@ __device__ void place_orders(EnvHdr& e, int al, int bl) {
   side_replace_order(e.side[1], e.bid_quote, P.order_size, &e.err);
 }
 
-// Intraday::DoAction (intraday.cpp:175-220)
-__device__ void do_action(EnvHdr& e, int action) {
+// Intraday::DoAction (intraday.cpp:175-220): action -> (ask_level, bid_level)
+__device__ __noinline__ void do_action(EnvHdr& e, int action) {
+  int al, bl;
   switch (action) {
-    case 0: place_orders(e, 1, 1); break;
-    case 1: clear_inventory(e); place_orders(e, e.ask_level, e.bid_level); break;
-    case 2: place_orders(e, 2, 2); break;
-    case 3: place_orders(e, 3, 3); break;
-    case 4: place_orders(e, 0, 2); break;
-    case 5: place_orders(e, 2, 0); break;
-    case 6: place_orders(e, 1, 4); break;
-    case 7: place_orders(e, 4, 1); break;
-    case 8: place_orders(e, 5, 5); break;
+    case 0: al = 1; bl = 1; break;
+    case 1: clear_inventory(e); al = e.ask_level; bl = e.bid_level; break;
+    case 2: al = 2; bl = 2; break;
+    case 3: al = 3; bl = 3; break;
+    case 4: al = 0; bl = 2; break;
+    case 5: al = 2; bl = 0; break;
+    case 6: al = 1; bl = 4; break;
+    case 7: al = 4; bl = 1; break;
+    case 8: al = 5; bl = 5; break;
+    default: return;
   }
+  place_orders(e, al, bl);
 }
 
 // Base::UpdateStats (base.cpp:412-442)
-__device__ void update_stats(EnvHdr& e) {
+__device__ __noinline__ void update_stats(EnvHdr& e) {
   e.ts_total++;
   bool has_ask = e.side[0].ord.live, has_bid = e.side[1].ord.live;
   if (has_ask) e.ts_ask++;
@@ -409,7 +412,7 @@ __device__ void update_stats(EnvHdr& e) {
 }
 
 // Intraday::UpdateBookProfiles for one row (intraday.cpp:274-313)
-__device__ void update_book_profiles(EnvHdr& e, const rlm_tick_msg& m) {
+__device__ __noinline__ void update_book_profiles(EnvHdr& e, const rlm_tick_msg& m) {
   e.last_date = e.date;
   e.date = m.date;
   e.time_ms = m.time_ms;
@@ -425,7 +428,7 @@ __device__ void update_book_profiles(EnvHdr& e, const rlm_tick_msg& m) {
 
 // Intraday::NextState (intraday.cpp:224-272) up to the window pushes; the eight values to
 // push are returned in pushv[W_MID..W_BIDTX] and applied lane-parallel by the caller.
-__device__ void next_state_scalar(EnvHdr& e, const rlm_tick_msg& m, double* pushv) {
+__device__ __noinline__ void next_state_scalar(EnvHdr& e, const rlm_tick_msg& m, double* pushv) {
   double mp = m_midprice(e);
   Fill au = side_apply_transactions<true>(e.side[0], m, mp, true);
   Fill bu = side_apply_transactions<false>(e.side[1], m, mp, true);
@@ -455,7 +458,7 @@ __device__ void next_state_scalar(EnvHdr& e, const rlm_tick_msg& m, double* push
 }
 
 // Intraday::getVariable (intraday.cpp:315-409)
-__device__ double get_variable(EnvHdr& e, const double* ring, int v) {
+__device__ __noinline__ double get_variable(EnvHdr& e, const double* ring, int v) {
   switch (v) {
     case RLM_VAR_POS: return (double)e.position / (double)P.order_size;
     case RLM_VAR_SPD: {

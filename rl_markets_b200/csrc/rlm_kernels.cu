@@ -22,15 +22,19 @@
 // [rndseq 8192][skellam 4096][pois30 4096][pois1p5 256] then per warp:
 // [EnvHdr+rings : env_stride][scratch : SCRATCH_BYTES]
 #define TABLE_BYTES (8192 + 4096 + 4096 + 256)
-#define VBUF_DOUBLES (2 * RLM_MAX_ACTIONS * 32)
-#define SCRATCH_MSG_OFF (VBUF_DOUBLES * 8)           // 4608: rlm_tick_msg (128 B)
-#define SCRATCH_PUSH_OFF (SCRATCH_MSG_OFF + 128)     // double pushv[RLM_NWIN]
-#define SCRATCH_VARS_OFF (SCRATCH_PUSH_OFF + 8 * RLM_NWIN)  // float to_vars[16]
-#define SCRATCH_Q_OFF (SCRATCH_VARS_OFF + 64)        // double q_pre_a[9], q_pre_b[9]
-#define SCRATCH_BYTES (SCRATCH_Q_OFF + 8 * 2 * RLM_MAX_ACTIONS + 16)
-
-size_t rlm_smem_bytes(int warps_per_cta, int env_stride) {
-  return TABLE_BYTES + (size_t)warps_per_cta * ((size_t)env_stride + (((size_t)SCRATCH_BYTES + 15) & ~(size_t)15));
+// per-warp scratch: [vbuf: (1 or 2) * A_max * VROW doubles][msg 128][pushv 10 doubles][to_vars 16 floats]
+//                   [q_pre_a, q_pre_b: 18 doubles][small set: 64 ints]
+#define SCR_MSG 0
+#define SCR_PUSH (SCR_MSG + 128)
+#define SCR_VARS (SCR_PUSH + 8 * RLM_NWIN)
+#define SCR_Q (SCR_VARS + 64)
+#define SCR_SS (SCR_Q + 8 * 2 * RLM_MAX_ACTIONS)
+#define SCR_VBUF (SCR_SS + 4 * SS_SLOTS)
+size_t rlm_scratch_bytes(int is_double) {
+  return ((size_t)SCR_VBUF + (size_t)(is_double ? 2 : 1) * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15;
+}
+size_t rlm_smem_bytes(int warps_per_cta, int env_stride, int scratch_bytes) {
+  return TABLE_BYTES + (size_t)warps_per_cta * ((size_t)env_stride + (size_t)scratch_bytes);
 }
 
 cudaError_t rlm_upload_params(const DevParams* p) { return cudaMemcpyToSymbol(P, p, sizeof(DevParams)); }
@@ -117,7 +121,7 @@ __global__ void rlm_clear_traces_kernel(DevPtrs ptr) {
 
 // ---------------------------------------------------------------------------------------------
 // parity record (include/rlm_record.h); lane 0 fills everything but the trace hash
-__device__ void fill_record(rlm_step_record* r, const EnvHdr& e, const float* to_vars, unsigned long long thash) {
+__device__ __noinline__ void fill_record(rlm_step_record* r, const EnvHdr& e, const float* to_vars, unsigned long long thash) {
   r->step = e.ep_step; r->action = e.cur_action; r->time_ms = e.time_ms; r->terminal = is_terminal(e) ? 1 : 0;
   r->position = e.position; r->ask_quote = e.ask_quote; r->bid_quote = e.bid_quote;
   r->ask_level = e.ask_level; r->bid_level = e.bid_level;
@@ -142,7 +146,7 @@ __device__ void fill_record(rlm_step_record* r, const EnvHdr& e, const float* to
 
 // Learner::_step up to the first NextState of performAction (serial.cpp:55-61, base.cpp:254-284);
 // lane 0.  Needs q_from / qb_from.  Returns false when the episode is over.
-__device__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, const DynParams& D) {
+__device__ __noinline__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, const DynParams& D) {
   if (is_terminal(e)) {
     clear_inventory(e);  // Runner::RunEpisode, serial.cpp:31
     e.phase = PH_DONE;
@@ -163,8 +167,12 @@ __device__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, const DynParam
   return true;
 }
 
+__device__ __noinline__ void flow_next_dev(rlm_flow_state* s, const int8_t* sk, const uint8_t* p30, const uint8_t* p15, rlm_tick_msg* m) {
+  rlm_flow_next(s, &P.flow, sk, p30, p15, m);
+}
+
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynParams D) {
+__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 14 ? 2 : 1)) rlm_tick_kernel(DevPtrs ptr, DynParams D) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned* s_rnd = (unsigned*)smem;
   int8_t* s_skellam = (int8_t*)(smem + 8192);
@@ -176,22 +184,25 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
   for (int i = tid; i < 256; i += WARPS * 32) s_pois1p5[i] = rlm_flow_pois1p5_lut[i];
   __syncthreads();
 
-  const int env = blockIdx.x * WARPS + warp;
-  if (env >= P.n_envs) return;
+  const int env_raw = blockIdx.x * WARPS + warp;
+  const bool active = env_raw < P.n_envs;
+  const int env = active ? env_raw : 0;
   const int stride = P.env_stride;
-  const size_t scratch_bytes = ((size_t)SCRATCH_BYTES + 15) & ~(size_t)15;
-  unsigned char* wbase = smem + TABLE_BYTES + (size_t)warp * (stride + scratch_bytes);
+  unsigned char* wbase = smem + TABLE_BYTES + (size_t)warp * (stride + P.scratch_bytes);
   EnvHdr& e = *(EnvHdr*)wbase;
   double* ring = (double*)(wbase + sizeof(EnvHdr));
   unsigned char* scratch = wbase + stride;
-  double* vbuf = (double*)scratch;
-  int* hs_keys = (int*)scratch;            // aliases vbuf (used at different times)
-  int* hs_vals = hs_keys + HS_SLOTS;
-  rlm_tick_msg& msg = *(rlm_tick_msg*)(scratch + SCRATCH_MSG_OFF);
-  double* pushv = (double*)(scratch + SCRATCH_PUSH_OFF);
-  float* to_vars = (float*)(scratch + SCRATCH_VARS_OFF);
-  double* q_pre_a = (double*)(scratch + SCRATCH_Q_OFF);
+  rlm_tick_msg& msg = *(rlm_tick_msg*)(scratch + SCR_MSG);
+  double* pushv = (double*)(scratch + SCR_PUSH);
+  float* to_vars = (float*)(scratch + SCR_VARS);
+  double* q_pre_a = (double*)(scratch + SCR_Q);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
+  int* sset = (int*)(scratch + SCR_SS);
+  double* vbuf = (double*)(scratch + SCR_VBUF);
+  if (!active) {  // tail warps only keep the CTA barriers balanced
+    if (D.tick_sync) for (int t = 0; t < D.n_ticks; ++t) __syncthreads();
+    return;
+  }
 
   // ---- stage the env record: coalesced 16-byte loads
   {
@@ -210,19 +221,23 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
   unsigned long long* mt_agt = ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr;
   const int A = P.n_actions;
   unsigned long long n_ticks_done = 0, n_steps_done = 0, sum_z = 0;
+  unsigned long long bases[3] = {0ull, 0ull, 0ull};
+  bool stopped = false;
 
 #pragma unroll 1
   for (int t = 0; t < D.n_ticks; ++t) {
+    if (D.tick_sync) __syncthreads();
     const int phase = e.phase;
-    if (phase == PH_DONE) break;
+    if (phase == PH_DONE || stopped) continue;
     // ---- tick message
     if (P.source == RLM_SOURCE_GENERATOR) {
-      if (lane == 0) rlm_flow_next(&e.flow, &P.flow, s_skellam, s_pois30, s_pois1p5, &msg);
+      if (lane == 0) flow_next_dev(&e.flow, s_skellam, s_pois30, s_pois1p5, &msg);
     } else {
       const int pos = D.stream_off + t;  // tick-synchronous: every env consumes the same tick index
       if (pos >= D.stream_ticks) {
         if (lane == 0) e.err |= ERR_STREAM_UNDERRUN;
-        break;
+        stopped = true;
+        continue;
       }
       const unsigned* src = (const unsigned*)(ptr.stream + ((size_t)pos * P.n_envs + env));
       ((unsigned*)&msg)[lane] = __ldg(src + lane);  // one 128-byte line per tick
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
       if (!full) continue;
       // serial.cpp:24-25,55-60: the first from-state is the never-populated State (all features 0)
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, e.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb);
+      eval_q(s_rnd, theta_a, theta_b, e.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false);
       if (lane < A) { e.q_from[lane] = qa; e.qb_from[lane] = qb; }
       __syncwarp();
       if (lane == 0) begin_step(e, mt_pol, D);
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
     // Q(to, .) under the current theta
     {
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, to_vars, P.n_state_vars, false, vbuf, lane, qa, qb);
+      eval_q(s_rnd, theta_a, theta_b, to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
       if (lane < A) { q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
     }
     __syncwarp();
@@ -357,8 +372,7 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
       const float rate = (float)pushv[0];
       const double scaled = pushv[1];
       double* th = (pushv[2] != 0.0) ? theta_b : theta_a;
-      __syncwarp();  // vbuf (aliased by the hash set) is free: eval_q finished with it
-      int nz = trace_pass(e, s_rnd, hs_keys, hs_vals, tf, te, th, e.cur_action, rate, scaled, lane);
+      int nz = trace_pass(e, sset, tf, te, th, e.cur_action, rate, scaled, lane);
       if (lane == 0) { e.n_traces = nz; e.sum_traces += nz; }
       sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
     }
@@ -375,11 +389,12 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
     }
     // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
     if (lane < RLM_N_STATE_MAX) e.from_vars[lane] = to_vars[lane];
+    e.from_base0[lane] = mod_m(bases[0]);  // group-0 partial hash of the new from-state (trace_pass)
     if (lane == 0) { e.null_from = 0; e.n_steps++; e.ep_step++; }
     __syncwarp();
     {
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, e.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb);
+      eval_q(s_rnd, theta_a, theta_b, e.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true);
       if (lane < A) { e.q_from[lane] = qa; e.qb_from[lane] = qb; }
     }
     __syncwarp();
@@ -405,8 +420,8 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_tick_kernel(DevPtrs ptr, DynPa
 
 // ---------------------------------------------------------------------------------------------
 template <int WARPS>
-static cudaError_t launch_tick(const DevPtrs& ptr, const DynParams& D, int n_envs, int env_stride, cudaStream_t st) {
-  size_t smem = rlm_smem_bytes(WARPS, env_stride);
+static cudaError_t launch_tick(const DevPtrs& ptr, const DynParams& D, int n_envs, int env_stride, int scratch_bytes, cudaStream_t st) {
+  size_t smem = rlm_smem_bytes(WARPS, env_stride, scratch_bytes);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(rlm_tick_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -418,12 +433,12 @@ static cudaError_t launch_tick(const DevPtrs& ptr, const DynParams& D, int n_env
   return cudaGetLastError();
 }
 
-cudaError_t rlm_launch_tick(const DevPtrs& ptr, const DynParams& D, int n_envs, int env_stride, int warps, cudaStream_t st) {
+cudaError_t rlm_launch_tick(const DevPtrs& ptr, const DynParams& D, int n_envs, int env_stride, int scratch_bytes, int warps, cudaStream_t st) {
   switch (warps) {
-    case 4: return launch_tick<4>(ptr, D, n_envs, env_stride, st);
-    case 8: return launch_tick<8>(ptr, D, n_envs, env_stride, st);
-    case 14: return launch_tick<14>(ptr, D, n_envs, env_stride, st);
-    case 16: return launch_tick<16>(ptr, D, n_envs, env_stride, st);
+    case 4: return launch_tick<4>(ptr, D, n_envs, env_stride, scratch_bytes, st);
+    case 8: return launch_tick<8>(ptr, D, n_envs, env_stride, scratch_bytes, st);
+    case 14: return launch_tick<14>(ptr, D, n_envs, env_stride, scratch_bytes, st);
+    case 16: return launch_tick<16>(ptr, D, n_envs, env_stride, scratch_bytes, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -59,6 +59,7 @@ struct EnvHdr {
   long long n_steps, n_ticks, sum_traces;
   int w_head[RLM_NWIN], w_count[RLM_NWIN];
   float from_vars[RLM_N_STATE_MAX + 3];  // state variables of the from-state
+  int from_base0[32];  // from-state, feature group 0: lane j's partial tile hash sum mod M
   int phase, last_action, lo_vol_step, cur_action;
   int ask_level, bid_level, date, last_date, time_ms;
   int null_from;  // from-state is the never-populated State of serial.cpp:14-15,55 (all features 0)
@@ -89,6 +90,7 @@ struct DevParams {
   long long pos_lb, pos_ub, memory_size;
   unsigned long long m_magic;  // floor(2^64 / M)
   int m_pow2;
+  int ra_m[RLM_MAX_ACTIONS];  // rndseq[(a + 449*4) & 2047] mod M: the action term of a group-0 tile hash
   float gl;  // (float)(gamma*lambda): Traces::decay(float rate)
   double gw[3], gamma;
   float damping, pos_weight, trd_weight, pnl_weight;
@@ -97,6 +99,7 @@ struct DevParams {
   int ring_total;       // doubles per env
   int env_stride;       // bytes per env record in HBM (multiple of 16)
   int trace_cap, record_envs, record_cap;
+  int scratch_bytes;    // per-warp shared-memory scratch (depends on is_double)
   long long env_index0;
   VenueD venue;
   rlm_flow_params flow;
@@ -108,6 +111,8 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int n_ticks;
   int stream_ticks;   // ticks in the resident stream chunk
   int stream_off;     // first tick of the chunk this launch consumes
+  int tick_sync;      // 1: CTA barrier per tick (keeps the CTA's warps on the same code)
+  int pad;
 };
 
 struct DevPtrs {

@@ -23,6 +23,17 @@ FLOW_CSV = os.path.join(REF_DIR, "flow_csv")
 _lib = None
 
 
+class BookOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("side", C.c_int32), ("px", C.c_double * 5), ("vol", C.c_int64 * 5),
+                ("n", C.c_int32), ("pad", C.c_int32), ("a", C.c_double), ("b", C.c_int64)]
+
+
+class BookResult(C.Structure):
+    _fields_ = [("r_volume", C.c_int64), ("r_proxy", C.c_double), ("r_value", C.c_double), ("r_ok", C.c_int32),
+                ("n_transacted", C.c_int32), ("order", abi.OrderRec), ("obs_value", C.c_double),
+                ("obs_volume", C.c_int64), ("total_volume", C.c_int64)]
+
+
 def build_port():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
 
@@ -76,8 +87,15 @@ def lib():
         L.lobo_uniform_real.argtypes = [C.c_uint64, C.c_int32]
         L.lobo_uniform_int.restype = C.c_uint32
         L.lobo_uniform_int.argtypes = [C.c_uint64, C.c_uint32, C.c_int32]
+        L.lobo_book_script.argtypes = [C.POINTER(BookOp), C.c_int32, C.POINTER(BookResult)]
         _lib = L
     return _lib
+
+
+def lib_generate(cfg, env_index, n_ticks):
+    """Synthetic flow through the product's host entry point rlm_flow_generate (no GPU needed)."""
+    from rl_markets_b200 import lib as rlm
+    return rlm.flow_generate(cfg.flow, env_index, 0, n_ticks)
 
 
 def generate_ticks(cfg, env_index, n_ticks):

@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/* from the UNMODIFIED reference compiled into oracle/_ref (run in the
+build container, where /root/reference exists; the fixtures are committed so that the GPU box,
+which has no reference tree, can check against them).
+
+  tests/golden/units.json          reference unit-level vectors (oracle/_ref/ref_units)
+  tests/golden/steps_<name>.bin    first N rlm_step_record of a reference run (oracle/_ref/ref_driver)
+  tests/golden/manifest.json       the configs that produced them
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as ol  # noqa: E402
+from rl_markets_b200 import abi, config  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+N_RECORDS = 400
+CASES = [
+    dict(name="q_learn_m65536", algo="q_learn", M=65536, flow_seed=7, env=0, ticks=2500, over={}),
+    dict(name="sarsa_m16384", algo="sarsa", M=16384, flow_seed=7, env=1, ticks=2500, over={}),
+    dict(name="double_q_m65536", algo="double_q_learn", M=65536, flow_seed=9, env=2, ticks=2500, over={}),
+    dict(name="q_learn_m5003_greedy", algo="q_learn", M=5003, flow_seed=11, env=3, ticks=2500,
+         over={"policy.eps_init": 0.05}),
+    dict(name="q_learn_m4096_random_init", algo="q_learn", M=4096, flow_seed=13, env=5, ticks=2500,
+         over={"learning.random_init": True, "debug.random_seed": 77}),
+]
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    units = subprocess.check_output([ol.REF_UNITS]).decode()
+    json.loads(units)
+    with open(os.path.join(GOLD, "units.json"), "w") as f:
+        f.write(units)
+    manifest = []
+    for c in CASES:
+        y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
+        # the reference seeds every generator with debug.random_seed (main.cpp:84-88); env b of a batch uses
+        # random_seed + b, so the single-env reference run for env b gets that seed
+        seed = y["debug"]["random_seed"] + c["env"]
+        y_run = json.loads(json.dumps(y))
+        y_run["debug"]["random_seed"] = seed
+        ref = ol.run_ref(y_run, c["flow_seed"], c["env"], c["ticks"])
+        recs = ref["records"][:N_RECORDS]
+        with open(os.path.join(GOLD, "steps_%s.bin" % c["name"]), "wb") as f:
+            for r in recs:
+                f.write(bytes(r))
+        manifest.append(dict(c, yaml=y, n_records=len(recs), summary=ref["summary"]))
+        print(c["name"], len(recs), "records;", ref["summary"]["steps"], "reference steps")
+    with open(os.path.join(GOLD, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
