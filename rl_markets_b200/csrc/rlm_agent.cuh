@@ -54,7 +54,7 @@ __device__ __noinline__ unsigned mt_uniform_int(unsigned long long* x, int& p, u
   return (unsigned)hi;
 }
 // glibc rand() (random_r TYPE_3)
-__device__ __noinline__ int crand_next(EnvHdr& e) {
+__device__ __noinline__ int crand_next(AgentD& e) {
   unsigned v = (unsigned)e.crand_r[e.crand_f] + (unsigned)e.crand_r[e.crand_b];
   e.crand_r[e.crand_f] = (int)v;
   int out = (int)(v >> 1);
@@ -65,13 +65,17 @@ __device__ __noinline__ int crand_next(EnvHdr& e) {
 
 // ------------------------------------------------------------------ windows (lane w = window w)
 // Accumulator<double>::push / RollingMean<double>::push (accumulators.cpp:17-27,86-109)
-__device__ __noinline__ void window_push(EnvHdr& e, double* ring, int w, double val) {
+// `old` = ring slot about to be overwritten (the oldest element when the window is full); callers
+// load the slots of all windows first so that the HBM/L2 round trips overlap.
+__device__ __forceinline__ double window_peek(const EnvHdr& e, const double* ring, int w) {
+  return ring[P.win_off[w] + e.w_head[w]];
+}
+__device__ __noinline__ void window_push(EnvHdr& e, double* ring, int w, double val, double old) {
   const int ws = P.win_size[w];
   double* r = ring + P.win_off[w];
   int head = e.w_head[w], cnt = e.w_count[w];
   double sum = e.w_sum[w], mean = e.w_mean[w], s = e.w_s[w];
   const bool overflow = (cnt == ws);
-  const double old = r[head];  // oldest element when full
   r[head] = val;
   head = head + 1 == ws ? 0 : head + 1;
   sum += val;
@@ -137,6 +141,34 @@ __device__ __forceinline__ double seg_sum(double acc, double w, const double* r)
 }
 // bases[g]: lane j's partial hash sum of group g; computed when !reuse, reused otherwise (the two
 // evaluations of one learner step -- before and after the weight update -- are on the same state).
+//
+// Software pipeline: the 9 (18 for double agents) gathers of group g+1 are issued -- back to back,
+// after ALL their indices are known, so that no shared-memory wait sits between two of them --
+// before group g is transposed and summed; the DRAM round trip of a group hides behind the
+// 32..64 dependent multiply-adds of the previous one.
+struct QGather { double a[RLM_MAX_ACTIONS]; double b[RLM_MAX_ACTIONS]; };
+
+__device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
+                                        bool null_state, int g, int lane, unsigned long long* bases, bool reuse, QGather& out) {
+  const int A = P.n_actions;
+  const float* gv = (g == 1) ? vars + 3 : vars;
+  const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
+  unsigned long long base = 0ull;
+  if (!null_state) {
+    if (reuse) base = bases[g];
+    else { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
+  }
+  int f[RLM_MAX_ACTIONS];
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.a[a] = (a < A) ? th_a[f[a]] : 0.0;  // plain (coherent) loads: theta is rewritten by trace_pass in this kernel
+  if (th_b) {
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.b[a] = (a < A) ? th_b[f[a]] : 0.0;
+  }
+}
+
 __device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
                        bool null_state, double* vbuf, int lane, double& qa_out, double& qb_out,
                        unsigned long long* bases, bool reuse) {
@@ -144,29 +176,16 @@ __device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, con
   double qa = 0.0, qb = 0.0;
   double* va = vbuf;
   double* vb = vbuf + RLM_MAX_ACTIONS * VROW;
-#pragma unroll 1
+  QGather cur, nxt;
+  q_issue(rnd, th_a, th_b, vars, n, null_state, 0, lane, bases, reuse, cur);
+#pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const float* gv = (g == 1) ? vars + 3 : vars;
-    const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
-    unsigned long long base = 0ull;
-    if (!null_state) {
-      if (reuse) base = bases[g];
-      else { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
-    }
-    double ta[RLM_MAX_ACTIONS], tb[RLM_MAX_ACTIONS];
+    if (g < 2) q_issue(rnd, th_a, th_b, vars, n, null_state, g + 1, lane, bases, reuse, nxt);
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
       if (a < A) {
-        int f = null_state ? 0 : tile_index(rnd, base, nf, g * A + a);
-        ta[a] = th_a[f];
-        if (th_b) tb[a] = th_b[f];
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
-      if (a < A) {
-        va[a * VROW + lane] = ta[a];
-        if (th_b) vb[a * VROW + lane] = tb[a];
+        va[a * VROW + lane] = cur.a[a];
+        if (th_b) vb[a * VROW + lane] = cur.b[a];
       }
     }
     __syncwarp();
@@ -183,13 +202,14 @@ __device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, con
       }
     }
     __syncwarp();
+    if (g < 2) cur = nxt;
   }
   qa_out = qa;
   qb_out = qb;
 }
 
 // argmax with rand() tie-breaks over q[0..A) (agent.cpp:144-169); lane 0
-__device__ __noinline__ int argmax_ties(EnvHdr& e, const double* q) {
+__device__ __noinline__ int argmax_ties(AgentD& e, const double* q) {
   int index = 0, n_ties = 1;
   double cur = q[0];
   for (int a = 1; a < P.n_actions; a++) {
@@ -205,7 +225,7 @@ __device__ __noinline__ int argmax_ties(EnvHdr& e, const double* q) {
   return index;
 }
 // Greedy::Sample (policy.cpp:37-55); lane 0
-__device__ __noinline__ int greedy_sample(EnvHdr& e, const double* qs) {
+__device__ __noinline__ int greedy_sample(AgentD& e, const double* qs) {
   int argmax = 0, n_ties = 1;
   for (int a = 1; a < P.n_actions; a++) {
     if (qs[a] > qs[argmax]) argmax = a;
@@ -217,7 +237,7 @@ __device__ __noinline__ int greedy_sample(EnvHdr& e, const double* qs) {
   return argmax;
 }
 // Agent::action / DoubleAgent::action + Policy::Sample; lane 0.  qa/qb: Q_A(s,.), Q_B(s,.)
-__device__ __noinline__ int policy_action(EnvHdr& e, const double* qa, const double* qb, unsigned long long* mt, const DynParams& D) {
+__device__ __noinline__ int policy_action(AgentD& e, const double* qa, const double* qb, unsigned long long* mt, const DynParams& D) {
   double qs[RLM_MAX_ACTIONS];
   for (int a = 0; a < P.n_actions; ++a) qs[a] = P.is_double ? (qa[a] + qb[a]) / 2.0 : qa[a];
   int pt = D.greedy ? RLM_POLICY_GREEDY : P.policy_type;
@@ -264,7 +284,7 @@ __device__ __forceinline__ int last_writer(const int* ss, int f, bool null_from)
   return la;
 }
 
-__device__ __noinline__ int trace_pass(EnvHdr& e, int* ss, int* tf, float* te, double* theta, int action, float rate,
+__device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, double* theta, int action, float rate,
                                        double scaled_update, int lane) {
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];

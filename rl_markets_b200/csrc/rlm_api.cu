@@ -35,7 +35,8 @@ struct rlm_handle_s {
   DynParams dyn;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  int warps = 14;
+  int n_sms = 148;
+  int ready_cap = 0;  // ticks per run call the ready counters can hold
   int n_policies = 1;
   size_t env_bytes = 0;
   rlm_tick_msg* d_stream = nullptr;
@@ -242,19 +243,17 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   h->alpha = cfg->alpha_start;
   h->eps = (double)cfg->eps_init;
   memset(&h->dyn, 0, sizeof(h->dyn));
-  // 14 warps per CTA, 2 CTAs per SM: 28 envs per SM, so 4096 envs are one wave of 148 SMs
-  h->warps = 14;
+  CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  CK(cudaMalloc(&h->ptr.ready, (size_t)cfg->n_envs * 4));
+  h->ready_cap = 256;
+  CK(cudaMalloc(&h->ptr.ready_count, (size_t)h->ready_cap * 4));
   {
     int dev_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-    while (h->warps > 4 && rlm_smem_bytes(h->warps, p.env_stride, p.scratch_bytes) > (size_t)dev_smem) h->warps = (h->warps == 14) ? 8 : 4;
-    if (rlm_smem_bytes(h->warps, p.env_stride, p.scratch_bytes) > (size_t)dev_smem)
-      return fail(RLM_ERR_UNSUPPORTED, "window lookbacks too large for shared memory staging");
+    if (rlm_agent_smem_bytes(8, p.scratch_bytes) > (size_t)dev_smem) return fail(RLM_ERR_UNSUPPORTED, "agent kernel shared memory exceeds the device limit");
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-  if (const char* s = getenv("RLM_TICK_SYNC")) h->dyn.tick_sync = atoi(s);
-  if (const char* s = getenv("RLM_WARPS")) { int w = atoi(s); if (w == 4 || w == 8 || w == 14 || w == 16) h->warps = w; }
   CK(cudaStreamSynchronize(h->stream));
   *out = h;
   return RLM_OK;
@@ -267,6 +266,7 @@ int rlm_destroy(rlm_handle h) {
   cudaFree(h->ptr.env); cudaFree(h->ptr.theta); cudaFree(h->ptr.theta_b); cudaFree(h->ptr.dtheta);
   cudaFree(h->ptr.trace_f); cudaFree(h->ptr.trace_e); cudaFree(h->ptr.mt_pol); cudaFree(h->ptr.mt_agt);
   cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters); cudaFree(h->d_stream);
+  cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (g_params_owner == h) g_params_owner = nullptr;
   delete h;
@@ -327,7 +327,23 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     d.stream_ticks = h->stream_ticks;
     h->stream_cursor += n_ticks;
   }
-  CK(rlm_launch_tick(h->ptr, d, h->cfg.n_envs, h->hp.env_stride, h->hp.scratch_bytes, h->warps, h->stream));
+  // two kernels per tick (env tick, then the learner step of the envs whose midprice moved), then one
+  // trailing env pass that only runs the pending action selections, so that the observable state
+  // after the call is "every env sits inside performAction's loop"
+  int done = 0;
+  while (done < n_ticks) {
+    const int chunk = std::min(n_ticks - done, h->ready_cap);
+    CK(cudaMemsetAsync(h->ptr.ready_count, 0, (size_t)chunk * 4, h->stream));
+    for (int t = 0; t < chunk; ++t) {
+      DynParams dt = d;
+      dt.stream_off = d.stream_off + done;
+      CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->stream));
+      CK(rlm_launch_agent(h->ptr, dt, h->cfg.n_envs, h->hp.scratch_bytes, t, h->n_sms, h->stream));
+      h->launches += 2;
+    }
+    done += chunk;
+  }
+  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 1, h->stream));
   h->launches++;
   return RLM_OK;
 }
@@ -385,7 +401,7 @@ int rlm_get_stats(rlm_handle h, int32_t env0, int32_t n, rlm_env_stats* out) {
     s.position = e.position;
     s.ask_transactions = e.side[0].n_transacted; s.bid_transactions = e.side[1].n_transacted;
     s.market_buys = e.market_buys; s.market_sells = e.market_sells;
-    s.total_ticks = e.ts_total; s.steps = e.ep_step;
+    s.total_ticks = e.ts_total; s.steps = e.ag.ep_step;
     s.terminal = e.phase == PH_DONE; s.phase = e.phase;
   }
   return RLM_OK;
@@ -397,7 +413,7 @@ int rlm_get_state(rlm_handle h, float* out) {
   int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
   if (rc) return rc;
   for (int i = 0; i < h->cfg.n_envs; ++i)
-    for (int k = 0; k < h->cfg.n_state_vars; ++k) out[(size_t)i * h->cfg.n_state_vars + k] = v[i].from_vars[k];
+    for (int k = 0; k < h->cfg.n_state_vars; ++k) out[(size_t)i * h->cfg.n_state_vars + k] = v[i].ag.from_vars[k];
   return RLM_OK;
 }
 int rlm_get_reward(rlm_handle h, double* out) {
@@ -405,7 +421,7 @@ int rlm_get_reward(rlm_handle h, double* out) {
   std::vector<EnvHdr> v;
   int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
   if (rc) return rc;
-  for (int i = 0; i < h->cfg.n_envs; ++i) out[i] = v[i].last_reward;
+  for (int i = 0; i < h->cfg.n_envs; ++i) out[i] = v[i].ag.last_reward;
   return RLM_OK;
 }
 int rlm_get_actions(rlm_handle h, int32_t* out) {

@@ -1,11 +1,11 @@
 // rlm_types.h -- device-side data layout of the batched LOB environment + agent.
 //
-// One `EnvHdr` (+ its window rings) per environment, array-of-structs in HBM:
-// a warp owns one env for a whole launch, stages the record into shared memory
-// with coalesced 16-byte loads, runs `n_ticks` market ticks on it and writes it
-// back, so the env record costs 2*S bytes of HBM traffic per LAUNCH, not per
-// tick.  The big per-env arrays (theta, the compact trace list, the Mersenne
-// Twister state) stay in HBM and are touched sparsely.
+// One `EnvHdr` (+ its window rings) per environment, array-of-structs in HBM.
+// The env kernel (one thread per env) copies the header into thread-local
+// memory -- lane-interleaved, i.e. SoA across the warp -- for the scalar market
+// logic; the agent kernel (one warp per env) stages only the AgentD block into
+// shared memory.  The big per-env arrays (theta, the compact trace list, the
+// Mersenne Twister state) stay in HBM and are touched sparsely.
 #pragma once
 #include <stdint.h>
 #include "rlm.h"
@@ -45,6 +45,26 @@ struct SideD {  // market::Book<C,5> (include/market/book.h:22-110)
   OrderD ord;
 };
 
+// Agent-side per-env state.  The agent kernel stages exactly this block (16-byte aligned) into
+// shared memory; everything the learner step needs from the env is in here.
+struct alignas(16) AgentD {
+  double q_from[RLM_MAX_ACTIONS];   // Q_A(from, .) under the current theta
+  double qb_from[RLM_MAX_ACTIONS];  // Q_B(from, .) (double agents)
+  double last_reward, last_delta;
+  long long n_steps, sum_traces;
+  float from_vars[RLM_N_STATE_MAX + 3];  // state variables of the from-state
+  float to_vars[RLM_N_STATE_MAX + 3];    // state variables of the to-state (written by the env tick)
+  int from_base0[32];  // from-state, feature group 0: lane j's partial tile hash sum mod M
+  int crand_r[31];     // glibc rand() state
+  int crand_f, crand_b;
+  int mt_pol_idx, mt_agt_idx;  // std::mt19937_64::_M_p
+  int null_from;   // from-state is the never-populated State of serial.cpp:14-15,55 (all features 0)
+  int n_traces, cur_action;
+  int need_begin;  // the next env tick starts with Learner::_step's action selection (serial.cpp:55-61)
+  int kind;        // why the env is in the ready list: 0 learner step, 1 end of warm-up
+  int ep_step, err, pad;
+};
+
 struct EnvHdr {
   SideD side[2];  // 0 = ask, 1 = bid
   long long position;  // RiskManager::position_
@@ -52,26 +72,16 @@ struct EnvHdr {
   double agg_r, agg_pnl, agg_mpm;                            // locals of performAction kept across ticks
   double tp_val, ewma_up, ewma_dn;
   double ep_reward, ep_pnl, ep_bandh;
-  double last_reward, last_delta;
-  double q_from[RLM_MAX_ACTIONS];   // Q_A(from, .) under the current theta
-  double qb_from[RLM_MAX_ACTIONS];  // Q_B(from, .) (double agents)
   double w_sum[RLM_NWIN], w_mean[RLM_NWIN], w_s[RLM_NWIN];
-  long long n_steps, n_ticks, sum_traces;
+  long long n_ticks;
   int w_head[RLM_NWIN], w_count[RLM_NWIN];
-  float from_vars[RLM_N_STATE_MAX + 3];  // state variables of the from-state
-  int from_base0[32];  // from-state, feature group 0: lane j's partial tile hash sum mod M
-  int phase, last_action, lo_vol_step, cur_action;
+  int phase, last_action, lo_vol_step;
   int ask_level, bid_level, date, last_date, time_ms;
-  int null_from;  // from-state is the never-populated State of serial.cpp:14-15,55 (all features 0)
   int market_buys, market_sells;
   int ts_total, ts_ask, ts_bid, ts_both, ts_pos, ts_long, ts_short;
-  int ep_step, n_traces, err, stream_pos;
-  int mt_pol_idx, mt_agt_idx;  // std::mt19937_64::_M_p
-  int crand_f, crand_b;
-  int crand_r[31];
-  int pad0;
+  int err;
   rlm_flow_state flow;
-  int pad1;
+  AgentD ag;
 };
 
 struct VenueD {
@@ -128,4 +138,6 @@ struct DevPtrs {
   rlm_step_record* records;    // [record_envs][record_cap]
   int* record_count;           // [record_envs]
   unsigned long long* counters;  // [8]: ticks, steps, sum_traces, terminal, err
+  int* ready;                    // [n_envs] env indices that need the agent kernel this tick
+  int* ready_count;              // [ticks of the current run call]
 };

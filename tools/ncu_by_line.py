@@ -37,7 +37,7 @@ rows = list(csv.reader(open(csvp)))
 # pick the block belonging to the kernel
 start = None
 for i, r in enumerate(rows):
-    if r and r[0] == "Kernel Name":
+    if r and r[0] == "Kernel Name" and (os.environ.get("NCU_KERNEL", "") in r[1]):
         start = i
         break
 hdr = rows[start + 1]
