@@ -23,9 +23,11 @@ __device__ __noinline__ unsigned long long mt_next(unsigned long long* x, int& p
   const unsigned long long UM = 0xFFFFFFFF80000000ull, LM = 0x7FFFFFFFull, A = 0xB5026F5AA96619E9ull;
   int k1 = k + 1; if (k1 == 312) k1 = 0;
   int km = k + 156; if (km >= 312) km -= 312;
-  unsigned long long y = (x[k] & UM) | (x[k1] & LM);
-  unsigned long long z = x[km] ^ (y >> 1) ^ ((y & 1ull) ? A : 0ull);
-  x[k] = z;
+  // L2-coherent accesses: the policy generator is drawn from by env CTAs and by agent CTAs of the
+  // persistent kernel, which may run on different SMs
+  unsigned long long y = (__ldcg(x + k) & UM) | (__ldcg(x + k1) & LM);
+  unsigned long long z = __ldcg(x + km) ^ (y >> 1) ^ ((y & 1ull) ? A : 0ull);
+  __stcg(x + k, z);
   p = k + 1;   // stays in 1..312; 312 wraps on the next call
   z ^= (z >> 29) & 0x5555555555555555ull;
   z ^= (z << 17) & 0x71D67FFFEDA60000ull;
@@ -118,13 +120,13 @@ __device__ __noinline__ unsigned long long tile_base_sum(const unsigned* rnd, co
   for (int i = 0; i < nf; ++i) {
     int q = (int)floorf(vars[i] * (float)RLM_N_TILINGS);
     int c = tile_coord(q, i, j);
-    sum += rnd[(c + 449 * i) & 2047];
+    sum += __ldg(rnd + ((c + 449 * i) & 2047));
   }
-  sum += rnd[(j + 449 * nf) & 2047];
+  sum += __ldg(rnd + ((j + 449 * nf) & 2047));
   return sum;
 }
 __device__ __forceinline__ int tile_index(const unsigned* rnd, unsigned long long base, int nf, int h1) {
-  return mod_m(base + rnd[(h1 + 449 * (nf + 1)) & 2047]);
+  return mod_m(base + __ldg(rnd + ((h1 + 449 * (nf + 1)) & 2047)));
 }
 
 // Exact-order Q(s,a) for all actions (agent.cpp:117-135): lanes gather theta for their tiling,
@@ -162,10 +164,10 @@ __device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a,
 #pragma unroll
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
 #pragma unroll
-  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.a[a] = (a < A) ? th_a[f[a]] : 0.0;  // plain (coherent) loads: theta is rewritten by trace_pass in this kernel
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.a[a] = (a < A) ? __ldcg(th_a + f[a]) : 0.0;  // L2-coherent: theta is rewritten by trace_pass, possibly from another SM
   if (th_b) {
 #pragma unroll
-    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.b[a] = (a < A) ? th_b[f[a]] : 0.0;
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.b[a] = (a < A) ? __ldcg(th_b + f[a]) : 0.0;
   }
 }
 
@@ -258,9 +260,9 @@ __device__ __noinline__ int policy_action(AgentD& e, const double* qa, const dou
 // contains f (set if that action is the one taken, cleared otherwise).  Tile (j, a) of the
 // from-state is (b_j + r_a) mod M with b_j = lane j's partial hash sum mod M (EnvHdr::from_base0)
 // and r_a = rndseq[(a + 449*4) & 2047] mod M (DevParams::ra_m), so "f is a tile of action a" is
-// "(f - r_a) mod M is one of the 32 b_j": a 64-slot hash set of the b_j answers it with A probes.
-#define SS_SLOTS 64
-__device__ __forceinline__ unsigned ss_hash(int x) { return ((unsigned)x * 2654435761u) >> 26; }  // 6 bits
+// "(f - r_a) mod M is one of the 32 b_j": a 128-slot hash set of the b_j answers it with A probes.
+#define SS_SLOTS 128
+__device__ __forceinline__ unsigned ss_hash(int x) { return ((unsigned)x * 2654435761u) >> 25; }  // 7 bits
 __device__ __forceinline__ bool ss_member(const int* ss, int x) {
   unsigned slot = ss_hash(x);
   while (true) {
@@ -271,12 +273,12 @@ __device__ __forceinline__ bool ss_member(const int* ss, int x) {
   }
 }
 // last action whose group-0 tile list contains f, or -1
-__device__ __forceinline__ int last_writer(const int* ss, int f, bool null_from) {
+__device__ __forceinline__ int last_writer(const int* ss, int f, bool null_from, int a0 = 0) {
   const int A = P.n_actions;
   if (null_from) return f == 0 ? A - 1 : -1;  // every tile of every action is feature 0
   int la = -1;
 #pragma unroll 1
-  for (int a = 0; a < A; ++a) {
+  for (int a = a0; a < A; ++a) {
     int x = f - P.ra_m[a];
     if (x < 0) x += (int)P.memory_size;
     if (ss_member(ss, x)) la = a;
@@ -288,7 +290,7 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
                                        double scaled_update, int lane) {
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];
-  ss[lane] = HS_EMPTY; ss[lane + 32] = HS_EMPTY;
+  for (int i = lane; i < SS_SLOTS; i += 32) ss[i] = HS_EMPTY;
   __syncwarp();
   if (!null_from) {
     unsigned slot = ss_hash(b0);
@@ -307,17 +309,17 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
     for (int base = 0; base < n; base += 32) {
       int i = base + lane;
       bool valid = i < n;
-      int f = valid ? tf[i] : 0;
-      float ev = valid ? te[i] : 0.0f;
+      int f = valid ? __ldcg(tf + i) : 0;
+      float ev = valid ? __ldcg(te + i) : 0.0f;
       ev *= rate;
       bool keep = valid && !(ev < tol);
       if (keep) keep = last_writer(ss, f, null_from) < 0;
       unsigned mask = __ballot_sync(FULL, keep);
       int pos = w + __popc(mask & ((1u << lane) - 1u));
       if (keep) {
-        tf[pos] = f;
-        te[pos] = ev;
-        theta[f] += scaled_update * (double)ev;
+        __stcg(tf + pos, f);
+        __stcg(te + pos, ev);
+        atomicAdd(theta + f, scaled_update * (double)ev);  // one fp64 add performed at L2: same rounding as load-add-store
       }
       w += __popc(mask);
     }
@@ -329,7 +331,8 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
       f = b0 + P.ra_m[action];
       if (f >= (int)P.memory_size) f -= (int)P.memory_size;
     }
-    bool add = (last_writer(ss, f, null_from) == action);
+    // f is a tile of `action` by construction: only later actions can still clear it
+    bool add = null_from ? (action == P.n_actions - 1) : (last_writer(ss, f, false, action + 1) < 0);
     unsigned same = __match_any_sync(FULL, f);
     add = add && ((__ffs(same) - 1) == lane);
     unsigned mask = __ballot_sync(FULL, add);
@@ -341,9 +344,9 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
       total = P.trace_cap;
     }
     if (add) {
-      tf[pos] = f;
-      te[pos] = 1.0f;
-      theta[f] += scaled_update * (double)1.0f;
+      __stcg(tf + pos, f);
+      __stcg(te + pos, 1.0f);
+      atomicAdd(theta + f, scaled_update * (double)1.0f);
     }
     w = total;
   }
@@ -355,8 +358,8 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
 __device__ __noinline__ unsigned long long trace_hash(const int* tf, const float* te, const double* theta, int n, int lane) {
   unsigned long long h = 0;
   for (int i = lane; i < n; i += 32) {
-    int f = tf[i];
-    h += rlm_trace_mix((unsigned)f, __float_as_uint(te[i]), (unsigned long long)__double_as_longlong(theta[f]));
+    int f = __ldcg(tf + i);
+    h += rlm_trace_mix((unsigned)f, __float_as_uint(__ldcg(te + i)), (unsigned long long)__double_as_longlong(__ldcg(theta + f)));
   }
   for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(FULL, h, o);
   return h;

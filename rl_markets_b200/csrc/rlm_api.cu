@@ -36,6 +36,9 @@ struct rlm_handle_s {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   int n_sms = 148;
+  int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent (rlm_run_kernel)
+  int n_agent_ctas = 0;  // persistent engine: CTAs in the agent role
+  unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
   int ready_cap = 0;  // ticks per run call the ready counters can hold
   int n_policies = 1;
   size_t env_bytes = 0;
@@ -252,6 +255,26 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (rlm_agent_smem_bytes(8, p.scratch_bytes) > (size_t)dev_smem) return fail(RLM_ERR_UNSUPPORTED, "agent kernel shared memory exceeds the device limit");
   }
+  // persistent engine: queue + flags
+  {
+    int q = 1;
+    while (q < cfg->n_envs) q <<= 1;
+    h->ptr.q_size = q;
+    CK(cudaMalloc(&h->ptr.q_slots, (size_t)q * 4));
+    CK(cudaMemsetAsync(h->ptr.q_slots, 0xFF, (size_t)q * 4, h->stream));
+    CK(cudaMalloc(&h->ptr.ag_done, (size_t)cfg->n_envs * 4));
+    CK(cudaMemsetAsync(h->ptr.ag_done, 0, (size_t)cfg->n_envs * 4, h->stream));
+    CK(cudaMalloc(&h->d_qctl, 4 * 4));
+    h->ptr.q_head = h->d_qctl; h->ptr.q_tail = h->d_qctl + 1; h->ptr.env_warps_done = h->d_qctl + 2; h->ptr.q_done = (int*)(h->d_qctl + 3);
+    // agent CTAs must all be resident; leave at least a quarter of the slots to env CTAs
+    const int resident = rlm_run_max_resident_ctas(p.scratch_bytes, h->n_sms);
+    const int n_env_ctas = (cfg->n_envs + 127) / 128;
+    int want = (cfg->n_envs + 3) / 4;  // one agent warp per env at most
+    int cap = resident - std::min(n_env_ctas, std::max(resident / 4, 1));
+    h->n_agent_ctas = std::max(1, std::min(want, cap));
+    if (const char* s = getenv("RLM_AGENT_CTAS")) { int v = atoi(s); if (v > 0 && v < resident) h->n_agent_ctas = v; }
+    if (const char* s = getenv("RLM_ENGINE")) h->engine = (s[0] == 'p') ? 0 : 1;
+  }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   CK(cudaStreamSynchronize(h->stream));
@@ -267,6 +290,7 @@ int rlm_destroy(rlm_handle h) {
   cudaFree(h->ptr.trace_f); cudaFree(h->ptr.trace_e); cudaFree(h->ptr.mt_pol); cudaFree(h->ptr.mt_agt);
   cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters); cudaFree(h->d_stream);
   cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count);
+  cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (g_params_owner == h) g_params_owner = nullptr;
   delete h;
@@ -326,6 +350,13 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     d.stream_off = h->stream_cursor;
     d.stream_ticks = h->stream_ticks;
     h->stream_cursor += n_ticks;
+  }
+  if (h->engine == 0) {
+    // persistent engine: one launch, no global barrier between ticks
+    CK(cudaMemsetAsync(h->d_qctl, 0, 16, h->stream));
+    CK(rlm_launch_run(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, h->n_agent_ctas, h->stream));
+    h->launches += 1;
+    return RLM_OK;
   }
   // two kernels per tick (env tick, then the learner step of the envs whose midprice moved), then one
   // trailing env pass that only runs the pending action selections, so that the observable state

@@ -24,7 +24,7 @@
 #include "rlm_agent.cuh"
 #include "rlm_kernels.h"
 
-// ---- agent kernel shared memory: [rndseq 8192] then per warp [AgentD][scratch]
+// ---- agent-role shared memory: per warp [AgentD][scratch]  (the 8 KB hashing table is read through L1)
 // per-warp scratch: [q_pre_a, q_pre_b: 18 doubles][small set: 64 ints][vbuf: (1|2) * A_max * VROW doubles]
 #define SCR_Q 0
 #define SCR_SS (SCR_Q + 8 * 2 * RLM_MAX_ACTIONS)
@@ -34,7 +34,7 @@ size_t rlm_scratch_bytes(int is_double) {
   return ((size_t)SCR_VBUF + (size_t)(is_double ? 2 : 1) * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15;
 }
 size_t rlm_agent_smem_bytes(int warps_per_cta, int scratch_bytes) {
-  return 8192 + (size_t)warps_per_cta * (AG_BYTES + (size_t)scratch_bytes);
+  return (size_t)warps_per_cta * (AG_BYTES + (size_t)scratch_bytes);
 }
 
 cudaError_t rlm_upload_params(const DevParams* p) { return cudaMemcpyToSymbol(P, p, sizeof(DevParams)); }
@@ -325,98 +325,262 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
   out[2] = (double)table;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rlm_agent_kernel(DevPtrs ptr, DynParams D, int tslot) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  unsigned* s_rnd = (unsigned*)smem;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 2048; i += WARPS * 32) s_rnd[i] = rlm_rndseq_table[i];
-  __syncthreads();
-  unsigned char* wbase = smem + 8192 + (size_t)warp * (AG_BYTES + P.scratch_bytes);
-  AgentD& ag = *(AgentD*)wbase;
-  unsigned char* scratch = wbase + AG_BYTES;
+// The learner step of one ready env, by one warp.  `ag` / `scratch` are this warp's shared memory.
+__device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynParams& D, int env, AgentD& ag, unsigned char* scratch,
+                                               int lane, unsigned long long& steps_done, unsigned long long& sum_z) {
+  const unsigned* s_rnd = rlm_rndseq_table;
   double* q_pre_a = (double*)(scratch + SCR_Q);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   int* sset = (int*)(scratch + SCR_SS);
   double* vbuf = (double*)(scratch + SCR_VBUF);
   double* dec = vbuf;  // 3 doubles handed from lane 0 to the warp (vbuf is free between the evaluations)
   const int A = P.n_actions;
+  EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
+  {  // stage the agent block: coalesced 16-byte L2 loads (the block was written by another SM)
+    const int4* src = (const int4*)&g->ag;
+    int4* dst = (int4*)&ag;
+    for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) dst[i] = __ldcg(src + i);
+  }
+  __syncwarp();
+  const size_t pol = P.shared_policy ? 0 : (size_t)env;
+  double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
+  double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
+  unsigned long long bases[3];
+  if (ag.kind == 1) {
+    // end of warm-up: Q(null state, .) for the very first action selection
+    double qa, qb;
+    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false);
+    if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+    if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; }
+  } else {
+    int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
+    float* te = ptr.trace_e + (size_t)env * P.trace_cap;
+    {  // Q(to, .) under the current theta
+      double qa, qb;
+      eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
+      if (lane < A) { q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
+    }
+    __syncwarp();
+    if (lane == 0)
+      td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr, D, dec);
+    __syncwarp();
+    {
+      const float rate = (float)dec[0];
+      const double scaled = dec[1];
+      double* th = (dec[2] != 0.0) ? theta_b : theta_a;
+      __syncwarp();
+      int nz = trace_pass(ag, sset, tf, te, th, ag.cur_action, rate, scaled, lane);
+      if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
+      sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
+    }
+    __syncwarp();
+    __threadfence();  // theta updates (L2 atomics) are ordered before the re-evaluation below
+    if (env < P.record_envs) {  // parity record: the env part is read back from HBM (published by the env thread)
+      unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
+      if (lane == 0) {
+        EnvHdr tmp;
+        {
+          const int4* src = (const int4*)g;
+          int4* dst = (int4*)&tmp;
+          for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
+        }
+        int c = ptr.record_count[env];
+        if (c < P.record_cap) fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h);
+        ptr.record_count[env] = c + 1;
+      }
+    }
+    // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
+    if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+    ag.from_base0[lane] = mod_m(bases[0]);
+    if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+    __syncwarp();
+    {
+      double qa, qb;
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true);
+      if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+    }
+    steps_done++;
+  }
+  __syncwarp();
+  {  // write the agent block back
+    int4* dst = (int4*)&g->ag;
+    const int4* src = (const int4*)&ag;
+    for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) __stcg(dst + i, src[i]);
+  }
+  __syncwarp();
+}
+
+// Tick-synchronous engine: one launch per tick after rlm_env_kernel.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rlm_agent_kernel(DevPtrs ptr, DynParams D, int tslot) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* wbase = smem + (size_t)warp * (AG_BYTES + P.scratch_bytes);
+  AgentD& ag = *(AgentD*)wbase;
+  unsigned char* scratch = wbase + AG_BYTES;
   const int n_ready = ptr.ready_count[tslot];
   unsigned long long steps_done = 0, sum_z = 0;
 #pragma unroll 1
-  for (int idx = blockIdx.x * WARPS + warp; idx < n_ready; idx += gridDim.x * WARPS) {
-    const int env = ptr.ready[idx];
-    EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
-    {  // stage the agent block: coalesced 16-byte loads
-      const int4* src = (const int4*)&g->ag;
-      int4* dst = (int4*)&ag;
-      for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
-    const size_t pol = P.shared_policy ? 0 : (size_t)env;
-    double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
-    double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
-    unsigned long long bases[3];
-    if (ag.kind == 1) {
-      // end of warm-up: Q(null state, .) for the very first action selection
-      double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false);
-      if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
-      if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; }
-    } else {
-      int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
-      float* te = ptr.trace_e + (size_t)env * P.trace_cap;
-      {  // Q(to, .) under the current theta
-        double qa, qb;
-        eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
-        if (lane < A) { q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
-      }
-      __syncwarp();
-      if (lane == 0)
-        td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr, D, dec);
-      __syncwarp();
-      {
-        const float rate = (float)dec[0];
-        const double scaled = dec[1];
-        double* th = (dec[2] != 0.0) ? theta_b : theta_a;
-        __syncwarp();
-        int nz = trace_pass(ag, sset, tf, te, th, ag.cur_action, rate, scaled, lane);
-        if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
-        sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
-      }
-      __syncwarp();
-      if (env < P.record_envs) {  // parity record: the env part is read from HBM (written by rlm_env_kernel)
-        unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
-        if (lane == 0) {
-          int c = ptr.record_count[env];
-          if (c < P.record_cap) fill_record(&ptr.records[(size_t)env * P.record_cap + c], *g, ag, h);
-          ptr.record_count[env] = c + 1;
-        }
-      }
-      // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
-      if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
-      ag.from_base0[lane] = mod_m(bases[0]);
-      if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
-      __syncwarp();
-      {
-        double qa, qb;
-        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true);
-        if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
-      }
-      steps_done++;
-    }
-    __syncwarp();
-    {  // write the agent block back
-      int4* dst = (int4*)&g->ag;
-      const int4* src = (const int4*)&ag;
-      for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
-  }
+  for (int idx = blockIdx.x * WARPS + warp; idx < n_ready; idx += gridDim.x * WARPS)
+    agent_process_env(ptr, D, ptr.ready[idx], ag, scratch, lane, steps_done, sum_z);
   if (lane == 0 && (steps_done | sum_z)) {
     atomicAdd(&ptr.counters[1], steps_done);
     atomicAdd(&ptr.counters[2], sum_z);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent engine: ONE launch runs `n_ticks` ticks of every env with no global barrier.
+//   CTAs [0, n_agent_ctas)   agent role: warps pop env ids from a queue in HBM and run the learner step;
+//   CTAs [n_agent_ctas, ...)  env role: one thread per env; an env whose step ended publishes its agent
+//                             block, pushes its id and waits for the done flag while the other lanes of
+//                             its warp keep ticking.  Envs advance at their own pace (their results do
+//                             not depend on the schedule: all state is per env).
+// Agent CTAs come first in the grid, so they are resident before any env CTA can wait on them.
+#define RUN_THREADS 128
+#define RUN_WARPS (RUN_THREADS / 32)
+
+__device__ __forceinline__ void copy_ag_from_global(AgentD& dst, const AgentD* src) {
+  const int4* s = (const int4*)src;
+  int4* d = (int4*)&dst;
+#pragma unroll 4
+  for (int i = 0; i < (int)(sizeof(AgentD) / 16); ++i) d[i] = __ldcg(s + i);
+}
+
+__global__ void __launch_bounds__(RUN_THREADS, 4) rlm_run_kernel(DevPtrs ptr, DynParams D, int n_agent_ctas, int n_env_warps) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((int)blockIdx.x < n_agent_ctas) {
+    // ------------------------------------------------------------------ agent role
+    unsigned char* wbase = smem + (size_t)warp * (AG_BYTES + P.scratch_bytes);
+    AgentD& ag = *(AgentD*)wbase;
+    unsigned char* scratch = wbase + AG_BYTES;
+    unsigned long long steps_done = 0, sum_z = 0;
+    const unsigned qmask = (unsigned)ptr.q_size - 1u;
+    while (true) {
+      int env = -1;
+      if (lane == 0) {
+        const unsigned ticket = atomicAdd(ptr.q_head, 1u);
+        volatile int* slot = ptr.q_slots + (ticket & qmask);
+        while (true) {
+          int v = *slot;
+          if (v >= 0) { env = v; *slot = -1; break; }
+          if (*(volatile int*)ptr.q_done) {
+            const unsigned tail = *(volatile unsigned*)ptr.q_tail;
+            if ((int)(ticket - tail) >= 0) { env = -2; break; }  // every push is already consumed or owned
+          }
+          __nanosleep(200);
+        }
+      }
+      env = __shfl_sync(FULL, env, 0);
+      if (env < 0) break;
+      __threadfence();  // acquire: the env record published before the push
+      agent_process_env(ptr, D, env, ag, scratch, lane, steps_done, sum_z);
+      __threadfence();  // release: agent block, theta, traces
+      if (lane == 0) *(volatile int*)(ptr.ag_done + env) = 1;
+    }
+    if (lane == 0 && (steps_done | sum_z)) {
+      atomicAdd(&ptr.counters[1], steps_done);
+      atomicAdd(&ptr.counters[2], sum_z);
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- env role
+  const int b = ((int)blockIdx.x - n_agent_ctas) * RUN_THREADS + tid;
+  const bool valid = b < P.n_envs;
+  EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)(valid ? b : 0) * P.env_stride);
+  double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
+  EnvHdr e;
+  int ticks_left = 0, tick_idx = 0;
+  bool waiting = false;
+  unsigned ticked = 0;
+  if (valid) {
+    e = *g;  // thread-local copy (lane-interleaved local memory), kept for the whole launch
+    if (e.phase != PH_DONE) ticks_left = D.n_ticks;
+  }
+  const unsigned qmask = (unsigned)ptr.q_size - 1u;
+  while (true) {
+    if (waiting && *(volatile int*)(ptr.ag_done + b)) {
+      __threadfence();
+      *(volatile int*)(ptr.ag_done + b) = 0;
+      copy_ag_from_global(e.ag, &g->ag);
+      waiting = false;
+      begin_step(e, ptr.mt_pol + (size_t)b * 312, D);
+      e.ag.need_begin = 0;
+      if (e.phase == PH_DONE) ticks_left = 0;
+    }
+    bool push = false;
+    if (!waiting && ticks_left > 0) {
+      rlm_tick_msg msg;
+      bool have = true;
+      if (P.source == RLM_SOURCE_GENERATOR) {
+        flow_next_dev(&e.flow, &msg);
+      } else {
+        const int pos = D.stream_off + tick_idx;
+        if (pos >= D.stream_ticks) { e.err |= ERR_STREAM_UNDERRUN; have = false; ticks_left = 0; }
+        else {
+          const int4* src = (const int4*)(ptr.stream + ((size_t)pos * P.n_envs + b));
+          int4* dst = (int4*)&msg;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = __ldg(src + i);
+        }
+      }
+      if (have) {
+        const int was = e.phase;
+        const int r = env_tick(e, ring, msg);
+        ticks_left--; tick_idx++;
+        if (was != PH_PREOPEN) ticked++;
+        if (r >= 0) {
+          // publish what the agent warp needs (the whole record for envs with a parity dump)
+          if (b < P.record_envs) *g = e; else g->ag = e.ag;
+          __threadfence();
+          push = true;
+          waiting = true;
+        }
+      }
+    }
+    const unsigned pm = __ballot_sync(FULL, push);
+    if (pm) {
+      const int leader = __ffs(pm) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(ptr.q_tail, (unsigned)__popc(pm));
+      base = __shfl_sync(FULL, base, leader);
+      if (push) *(volatile int*)(ptr.q_slots + ((base + __popc(pm & ((1u << lane) - 1u))) & qmask)) = b;
+    }
+    if (!__any_sync(FULL, waiting || ticks_left > 0)) break;
+  }
+  unsigned errs = 0;
+  if (valid) { errs = (unsigned)(e.err | e.ag.err); *g = e; }
+  for (int o = 16; o > 0; o >>= 1) { ticked += __shfl_xor_sync(FULL, ticked, o); errs |= __shfl_xor_sync(FULL, errs, o); }
+  if (lane == 0) {
+    if (ticked) atomicAdd(&ptr.counters[0], (unsigned long long)ticked);
+    if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
+    __threadfence();
+    if (atomicAdd(ptr.env_warps_done, 1u) + 1u == (unsigned)n_env_warps) {
+      __threadfence();
+      *(volatile int*)ptr.q_done = 1;
+    }
+  }
+}
+
+cudaError_t rlm_launch_run(const DevPtrs& ptr, const DynParams& D, int n_envs, int scratch_bytes, int n_agent_ctas, cudaStream_t st) {
+  size_t smem = rlm_agent_smem_bytes(RUN_WARPS, scratch_bytes);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(rlm_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  const int n_env_ctas = (n_envs + RUN_THREADS - 1) / RUN_THREADS;
+  rlm_run_kernel<<<n_agent_ctas + n_env_ctas, RUN_THREADS, smem, st>>>(ptr, D, n_agent_ctas, n_env_ctas * RUN_WARPS);
+  return cudaGetLastError();
+}
+int rlm_run_max_resident_ctas(int scratch_bytes, int n_sms) {
+  int per_sm = 0;
+  size_t smem = rlm_agent_smem_bytes(RUN_WARPS, scratch_bytes);
+  cudaFuncSetAttribute(rlm_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rlm_run_kernel, RUN_THREADS, smem) != cudaSuccess) per_sm = 1;
+  return per_sm * n_sms;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -473,9 +637,7 @@ __global__ void k_test_to_price(const int* ticks, int n, double* out) {
 }
 // one warp per state: all tile indices, out[s][a][96]
 __global__ void k_test_tiles(const float* vars, int n, int* out) {
-  __shared__ unsigned s_rnd[2048];
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_rnd[i] = rlm_rndseq_table[i];
-  __syncthreads();
+  const unsigned* s_rnd = rlm_rndseq_table;
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const float* v = vars + (size_t)warp * P.n_state_vars;

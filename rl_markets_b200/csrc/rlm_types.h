@@ -140,4 +140,13 @@ struct DevPtrs {
   unsigned long long* counters;  // [8]: ticks, steps, sum_traces, terminal, err
   int* ready;                    // [n_envs] env indices that need the agent kernel this tick
   int* ready_count;              // [ticks of the current run call]
+  // persistent engine
+  int* q_slots;                  // [q_size] env ids handed from env threads to agent warps (-1 = empty)
+  unsigned* q_head;              // consumer tickets
+  unsigned* q_tail;              // producer tickets
+  unsigned* env_warps_done;
+  int* q_done;                   // set when every env warp has finished
+  int* ag_done;                  // [n_envs] agent -> env completion flags
+  int q_size;                    // power of two >= n_envs
+  int pad;
 };
