@@ -187,7 +187,13 @@ int rlm_read_records(rlm_handle h, int32_t env, rlm_step_record* out, int32_t ca
 
 /* raw device pointers, for torch.distributed / NCCL plumbing on the shared-policy path */
 int rlm_device_ptrs(rlm_handle h, void** theta, void** dtheta, int64_t* n_doubles);
-/* theta += dtheta; dtheta = 0 (after the all-reduce of dtheta) */
+/* Shared policy (cfg.shared_policy = 1; reference analogue: threads sharing one rl::Agent*,
+ * src/main.cpp:196-206).  One training tick across GPUs is
+ *   rlm_shared_tick_accumulate(h)   env tick + learner steps under theta_t, updates summed into dtheta
+ *   all-reduce(dtheta, SUM)         caller's collective (torch.distributed / NCCL) on rlm_device_ptrs()
+ *   rlm_apply_dtheta(h)             theta += dtheta; dtheta = 0; Q(from,.) under theta_{t+1}; next actions
+ * On one GPU rlm_run_ticks does the same without the collective. */
+int rlm_shared_tick_accumulate(rlm_handle h);
 int rlm_apply_dtheta(rlm_handle h);
 /* run on a caller-provided CUDA stream (cudaStream_t as void*); 0 = the handle's own stream */
 int rlm_set_stream(rlm_handle h, void* cuda_stream);

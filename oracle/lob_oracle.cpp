@@ -658,6 +658,11 @@ struct lobo_env {
   State *state = nullptr, *last_state = nullptr;
   Traces traces;
   std::vector<double> theta, theta_b;
+  // shared-policy batch: theta lives in the batch object, updates go to dtheta
+  std::vector<double>*sh_a = nullptr, *sh_b = nullptr, *sh_da = nullptr, *sh_db = nullptr;
+  std::vector<double>& THA() { return sh_a ? *sh_a : theta; }
+  std::vector<double>& THB() { return sh_b ? *sh_b : theta_b; }
+  bool is_double() const { return c.algorithm == RLM_ALGO_DOUBLE_Q_LEARN || c.algorithm == RLM_ALGO_DOUBLE_R_LEARN; }
   double alpha = 0, eps = 0, eps_init = 0, eps_floor = 0;
   bool greedy = false;
   MT64 policy_gen, agent_gen;
@@ -688,11 +693,11 @@ struct lobo_env {
     tp_val = -1.0;
     // agent.cpp:14-50
     uint32_t seed = c.random_seed + (uint32_t)idx;
-    theta.assign(c.memory_size, 0.0);
+    if (!sh_a) theta.assign(c.memory_size, 0.0);
     bool dbl = (c.algorithm == RLM_ALGO_DOUBLE_Q_LEARN || c.algorithm == RLM_ALGO_DOUBLE_R_LEARN);
     agent_gen.seed(seed);
     if (c.random_init) for (auto& t : theta) t = 2.0 * uniform_real01(agent_gen) - 1.0;  // agent.cpp:37-39
-    if (dbl) {
+    if (dbl && !sh_b) {
       theta_b.assign(c.memory_size, 0.0);
       if (c.random_init) for (auto& t : theta_b) t = 2.0 * uniform_real01(agent_gen) - 1.0;  // :190-192
     }
@@ -937,8 +942,8 @@ struct lobo_env {
     for (int i = T; i < 3 * T; i++) Q += w * th[features[i]];  // starts at T
     return Q;
   }
-  double getQ(State& s, int a) { return getQ_tab(theta, s, a); }
-  double getQb(State& s, int a) { return getQ_tab(theta_b, s, a); }
+  double getQ(State& s, int a) { return getQ_tab(THA(), s, a); }
+  double getQb(State& s, int a) { return getQ_tab(THB(), s, a); }
   int argmax_tab(const std::vector<double>& th, State& s) {  // :144-169 / :239-264
     int index = 0, n_ties = 1;
     double currMaxQ = getQ_tab(th, s, index);
@@ -954,8 +959,8 @@ struct lobo_env {
     }
     return index;
   }
-  int argmaxQ(State& s) { return argmax_tab(theta, s); }
-  int argmaxQb(State& s) { return argmax_tab(theta_b, s); }
+  int argmaxQ(State& s) { return argmax_tab(THA(), s); }
+  int argmaxQb(State& s) { return argmax_tab(THB(), s); }
   double maxQ(State& s) { return getQ(s, argmaxQ(s)); }  // :171-174
   void updateQ_tab(std::vector<double>& th, double update) {  // :137-142 / :232-237
     double scaled_update = update / c.n_tilings;
@@ -986,7 +991,7 @@ struct lobo_env {
   }
   unsigned agent_action(State& s) {  // Agent::action :67-74 / DoubleAgent::action :202-209
     std::vector<double> qs(c.n_actions, 0.0);
-    bool dbl = !theta_b.empty();
+    bool dbl = is_double();
     for (int a = 0; a < c.n_actions; a++) qs[a] = dbl ? (getQ(s, a) + getQb(s, a)) / 2.0f : getQ(s, a);
     return policy_sample(qs);
   }
@@ -1008,24 +1013,24 @@ struct lobo_env {
       case RLM_ALGO_Q_LEARN: {  // :282-292
         double Q = getQ(from, action);
         delta = reward + F_term + gamma * maxQ(to) - Q;
-        updateQ_tab(theta, alpha * delta);
+        updateQ_tab(sh_da ? *sh_da : theta, alpha * delta);
         return delta;
       }
       case RLM_ALGO_SARSA: {  // :300-311
         double Q1 = getQ(from, action), Q2 = getQ(to, (int)agent_action(to));
         delta = reward + F_term + gamma * Q2 - Q1;
-        updateQ_tab(theta, alpha * delta);
+        updateQ_tab(sh_da ? *sh_da : theta, alpha * delta);
         return delta;
       }
       case RLM_ALGO_DOUBLE_Q_LEARN: {  // :329-353
         if (uniform_real01(agent_gen) > 0.5) {
           double Qa = getQ(from, action);
           delta = reward + F_term + gamma * getQb(to, argmaxQ(to)) - Qa;
-          updateQ_tab(theta, alpha * delta);
+          updateQ_tab(sh_da ? *sh_da : theta, alpha * delta);
         } else {
           double Qb = getQb(from, action);
           delta = reward + F_term + gamma * getQ(to, argmaxQb(to)) - Qb;
-          updateQ_tab(theta_b, alpha * delta);
+          updateQ_tab(sh_db ? *sh_db : theta_b, alpha * delta);
         }
         return delta;
       }
@@ -1118,7 +1123,7 @@ struct lobo_env {
     uint64_t h = 0;
     for (int k = 0; k < traces.n; ++k) {
       int f = traces.nonzero[k];
-      uint32_t eb; uint64_t tb; float e = traces.eligibility[f]; double t = theta[f];
+      uint32_t eb; uint64_t tb; float e = traces.eligibility[f]; double t = THA()[f];
       memcpy(&eb, &e, 4); memcpy(&tb, &t, 8);
       h += rlm_trace_mix((uint32_t)f, eb, tb);
     }
@@ -1128,6 +1133,30 @@ struct lobo_env {
   bool windows_full() const {  // intraday.cpp:119-126
     return f_ask_transactions.full() && f_bid_transactions.full() && f_vwap_numer.full() && f_vwap_denom.full() &&
            f_volatility.full() && f_midprice.full() && tp_window.full() && spread_window.full();
+  }
+
+  // shared-policy batch: one tick; returns true when a learner step ended and begin_step() is pending
+  // (it must run only after the batch applied theta += dtheta)
+  bool tick_deferred(const rlm_tick_msg& m, rlm_step_record* rec) {
+    if (phase == PH_DONE) return false;
+    if (phase == PH_PREOPEN) {
+      Tx none;
+      UpdateBookProfiles(m, none);
+      if (market.IsOpen()) phase = PH_WARMUP;
+      return false;
+    }
+    if (phase == PH_WARMUP) {
+      NextState(m);
+      if (windows_full()) {
+        place_orders(1, 1);
+        newState(last_state);
+        phase = PH_RUN;
+        begin_step();  // Q(null state) under theta_t: nothing to wait for
+      }
+      return false;
+    }
+    if (run_tick(m)) { end_step(rec); return true; }
+    return false;
   }
 
   int64_t run(const rlm_tick_msg* msgs, int64_t n_msgs, int64_t max_steps, rlm_step_record* recs, int64_t rec_cap,
@@ -1242,6 +1271,56 @@ int64_t lobo_run_batch(const rlm_config* cfg, int32_t n_envs, int64_t n_ticks, i
   if (total_ticks) *total_ticks = k;
   return s;
 }
+
+// ---- shared-policy batch (the reference analogue is threads sharing one Agent*, src/main.cpp:196-206;
+// this synchronous formulation -- all envs of a tick read theta_t, theta_{t+1} = theta_t + sum of their
+// updates -- is the new algorithm of SURVEY section 8e, restated here as its CPU oracle)
+struct lobo_batch {
+  rlm_config c;
+  std::vector<lobo_env*> envs;
+  std::vector<double> th_a, th_b, d_a, d_b;
+  std::vector<int> pending;
+};
+
+lobo_batch* lobo_batch_create(const rlm_config* cfg) {
+  lobo_batch* b = new lobo_batch();
+  b->c = *cfg;
+  bool dbl = (cfg->algorithm == RLM_ALGO_DOUBLE_Q_LEARN);
+  b->th_a.assign(cfg->memory_size, 0.0); b->d_a.assign(cfg->memory_size, 0.0);
+  if (dbl) { b->th_b.assign(cfg->memory_size, 0.0); b->d_b.assign(cfg->memory_size, 0.0); }
+  for (int i = 0; i < cfg->n_envs; ++i) {
+    rlm_config one = *cfg;
+    one.memory_size = cfg->memory_size;
+    lobo_env* e = new lobo_env();
+    e->sh_a = &b->th_a; e->sh_da = &b->d_a;
+    if (dbl) { e->sh_b = &b->th_b; e->sh_db = &b->d_b; }
+    e->init(&one, cfg->env_index0 + i);
+    b->envs.push_back(e);
+  }
+  return b;
+}
+void lobo_batch_destroy(lobo_batch* b) { for (auto* e : b->envs) delete e; delete b; }
+
+// phase A of one tick for every env: msgs[env]; step records (if recs) are written at recs[env*rec_cap + count[env]]
+void lobo_batch_accumulate(lobo_batch* b, const rlm_tick_msg* msgs, rlm_step_record* recs, int32_t* rec_count, int32_t rec_cap) {
+  b->pending.clear();
+  for (size_t i = 0; i < b->envs.size(); ++i) {
+    rlm_step_record* r = nullptr;
+    if (recs && rec_count[i] < rec_cap) r = &recs[i * (size_t)rec_cap + rec_count[i]];
+    if (b->envs[i]->tick_deferred(msgs[i], r)) { b->pending.push_back((int)i); if (r) rec_count[i]++; }
+  }
+}
+double* lobo_batch_dtheta(lobo_batch* b, int table) { return table == 0 ? b->d_a.data() : (b->d_b.empty() ? nullptr : b->d_b.data()); }
+double* lobo_batch_theta(lobo_batch* b, int table) { return table == 0 ? b->th_a.data() : (b->th_b.empty() ? nullptr : b->th_b.data()); }
+// phase B: theta += dtheta; dtheta = 0; pending envs select their next action under the new theta
+void lobo_batch_apply(lobo_batch* b) {
+  for (size_t i = 0; i < b->th_a.size(); ++i) { b->th_a[i] += b->d_a[i]; b->d_a[i] = 0.0; }
+  for (size_t i = 0; i < b->th_b.size(); ++i) { b->th_b[i] += b->d_b[i]; b->d_b[i] = 0.0; }
+  for (int i : b->pending) b->envs[i]->begin_step();
+  b->pending.clear();
+}
+int64_t lobo_batch_steps(lobo_batch* b) { int64_t s = 0; for (auto* e : b->envs) s += e->total_steps; return s; }
+void lobo_batch_stats(lobo_batch* b, int32_t env, rlm_env_stats* out) { lobo_stats(b->envs[env], out); }
 
 int32_t lobo_to_ticks(const rlm_config* cfg, double px) { Venue v; v.init(cfg); return v.ToTicks(px); }
 double lobo_to_price(const rlm_config* cfg, int32_t ticks) { Venue v; v.init(cfg); return v.ToPrice(ticks); }

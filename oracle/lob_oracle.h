@@ -50,6 +50,17 @@ void lobo_go_greedy(lobo_env* e);
 int64_t lobo_run_batch(const rlm_config* cfg, int32_t n_envs, int64_t n_ticks, int32_t n_threads,
                        int64_t* total_ticks, double* seconds);
 
+/* ---- shared-policy batch: synchronous formulation, see lob_oracle.cpp ---- */
+typedef struct lobo_batch lobo_batch;
+lobo_batch* lobo_batch_create(const rlm_config* cfg);
+void lobo_batch_destroy(lobo_batch* b);
+void lobo_batch_accumulate(lobo_batch* b, const rlm_tick_msg* msgs /* [n_envs] */, rlm_step_record* recs, int32_t* rec_count, int32_t rec_cap);
+double* lobo_batch_dtheta(lobo_batch* b, int table);
+double* lobo_batch_theta(lobo_batch* b, int table);
+void lobo_batch_apply(lobo_batch* b);
+int64_t lobo_batch_steps(lobo_batch* b);
+void lobo_batch_stats(lobo_batch* b, int32_t env, rlm_env_stats* out);
+
 /* ---- unit-level entry points (golden vectors) ---- */
 int32_t lobo_to_ticks(const rlm_config* cfg, double px);
 double lobo_to_price(const rlm_config* cfg, int32_t ticks);

@@ -39,6 +39,8 @@ struct rlm_handle_s {
   int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent (rlm_run_kernel)
   int n_agent_ctas = 0;  // persistent engine: CTAs in the agent role
   unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
+  DynParams shared_dyn;
+  bool in_run = false;
   int ready_cap = 0;  // ticks per run call the ready counters can hold
   int n_policies = 1;
   size_t env_bytes = 0;
@@ -102,7 +104,8 @@ static int derive(rlm_handle_s* h) {
   if (c.n_bands < 1 || c.n_bands > RLM_MAX_BANDS) return fail(RLM_ERR_INVALID_ARGUMENT, "bad venue table");
   if (c.order_size <= 0) return fail(RLM_ERR_RUNTIME, "Order size must be non-zero and positive.");
   if (c.tp_lookback < 1) return fail(RLM_ERR_INVALID_ARGUMENT, "target_price.lookback must be >= 1");
-  if (c.shared_policy) return fail(RLM_ERR_UNSUPPORTED, "shared_policy is not built yet in this round");
+  if (c.shared_policy && c.random_init) return fail(RLM_ERR_UNSUPPORTED, "shared_policy with random_init is not supported");
+  if (c.shared_policy && (c.memory_size & 1)) return fail(RLM_ERR_UNSUPPORTED, "shared_policy needs an even memory_size");
   p.n_envs = c.n_envs; p.n_actions = c.n_actions; p.algorithm = c.algorithm; p.policy_type = c.policy_type;
   p.reward_measure = c.reward_measure; p.n_state_vars = c.n_state_vars;
   for (int i = 0; i < c.n_state_vars; ++i) {
@@ -222,6 +225,11 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   if (p.is_double) {
     CK(cudaMalloc(&h->ptr.theta_b, th_bytes));
     CK(cudaMemsetAsync(h->ptr.theta_b, 0, th_bytes, h->stream));
+  }
+  if (cfg->shared_policy) {
+    size_t dbytes = (size_t)(p.is_double ? 2 : 1) * (size_t)p.memory_size * 8;
+    CK(cudaMalloc(&h->ptr.dtheta, dbytes));
+    CK(cudaMemsetAsync(h->ptr.dtheta, 0, dbytes, h->stream));
   }
   CK(cudaMalloc(&h->ptr.trace_f, (size_t)cfg->n_envs * p.trace_cap * 4));
   CK(cudaMalloc(&h->ptr.trace_e, (size_t)cfg->n_envs * p.trace_cap * 4));
@@ -351,6 +359,20 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     d.stream_ticks = h->stream_ticks;
     h->stream_cursor += n_ticks;
   }
+  if (h->cfg.shared_policy) {
+    // single-GPU shared policy: every tick = accumulate, apply (no all-reduce needed)
+    const DynParams keep = h->dyn;
+    h->in_run = true;
+    for (int t = 0; t < n_ticks; ++t) {
+      h->dyn = keep; h->dyn.stream_off = d.stream_off + t; h->dyn.stream_ticks = d.stream_ticks;
+      int rc2 = rlm_shared_tick_accumulate(h);
+      if (!rc2) rc2 = rlm_apply_dtheta(h);
+      if (rc2) { h->dyn = keep; h->in_run = false; return rc2; }
+    }
+    h->dyn = keep;
+    h->in_run = false;
+    return RLM_OK;
+  }
   if (h->engine == 0) {
     // persistent engine: one launch, no global barrier between ticks
     CK(cudaMemsetAsync(h->d_qctl, 0, 16, h->stream));
@@ -369,7 +391,7 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
       DynParams dt = d;
       dt.stream_off = d.stream_off + done;
       CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->stream));
-      CK(rlm_launch_agent(h->ptr, dt, h->cfg.n_envs, h->hp.scratch_bytes, t, h->n_sms, h->stream));
+      CK(rlm_launch_agent(h->ptr, dt, h->cfg.n_envs, h->hp.scratch_bytes, t, h->n_sms, 0, h->stream));
       h->launches += 2;
     }
     done += chunk;
@@ -523,12 +545,50 @@ int rlm_device_ptrs(rlm_handle h, void** theta, void** dtheta, int64_t* n_double
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   if (theta) *theta = h->ptr.theta;
   if (dtheta) *dtheta = h->ptr.dtheta;
-  if (n_doubles) *n_doubles = (int64_t)h->n_policies * h->cfg.memory_size;
+  // dtheta holds table A then table B (double agents): all-reduce n_doubles values starting at *dtheta
+  if (n_doubles) *n_doubles = h->cfg.shared_policy ? (int64_t)(h->hp.is_double ? 2 : 1) * h->cfg.memory_size : (int64_t)h->n_policies * h->cfg.memory_size;
   return RLM_OK;
 }
+// Shared policy, phase A of one tick: env tick + learner steps evaluated under theta_t, updates
+// accumulated into dtheta.  The caller all-reduces dtheta (rlm_device_ptrs) across ranks when the policy
+// spans GPUs, then calls rlm_apply_dtheta.
+int rlm_shared_tick_accumulate(rlm_handle h) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->cfg.shared_policy) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was not created with shared_policy");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = upload_params(h);
+  if (rc) return rc;
+  DynParams d = h->dyn;
+  d.alpha = h->alpha; d.eps = h->eps; d.n_ticks = 1;
+  if (h->cfg.source == RLM_SOURCE_STREAM && !h->in_run) {
+    if (h->stream_cursor + 1 > h->stream_ticks) return fail(RLM_ERR_END_OF_DATA, "not enough ticks loaded");
+    d.stream_off = h->stream_cursor; d.stream_ticks = h->stream_ticks;
+    h->stream_cursor += 1;
+  }
+  CK(cudaMemsetAsync(h->ptr.ready_count, 0, 4, h->stream));
+  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 0, h->stream));
+  CK(rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 1, h->stream));
+  h->launches += 2;
+  h->shared_dyn = d;
+  return RLM_OK;
+}
+
+// Shared policy, phase B: theta += dtheta; dtheta = 0; Q(from, .) under the new theta for the envs that
+// stepped; then their action selection (the trailing env pass).
 int rlm_apply_dtheta(rlm_handle h) {
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
-  return fail(RLM_ERR_UNSUPPORTED, "shared_policy is not built yet in this round");
+  if (!h->cfg.shared_policy) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was not created with shared_policy");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = upload_params(h);
+  if (rc) return rc;
+  const long long n = (long long)(h->hp.is_double ? 2 : 1) * h->cfg.memory_size;
+  CK(rlm_launch_apply_dtheta(h->ptr.theta, h->ptr.dtheta, h->cfg.memory_size, h->n_sms, h->stream));
+  if (h->hp.is_double) CK(rlm_launch_apply_dtheta(h->ptr.theta_b, h->ptr.dtheta + h->cfg.memory_size, h->cfg.memory_size, h->n_sms, h->stream));
+  (void)n;
+  CK(rlm_launch_agent(h->ptr, h->shared_dyn, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 2, h->stream));
+  CK(rlm_launch_env(h->ptr, h->shared_dyn, h->cfg.n_envs, 0, 1, h->stream));
+  h->launches += 3;
+  return RLM_OK;
 }
 
 int rlm_flow_generate(const rlm_flow_params* p, int64_t env_index, int64_t first_tick, int32_t n_ticks, rlm_tick_msg* out) {

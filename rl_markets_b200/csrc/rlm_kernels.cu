@@ -326,8 +326,11 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
 }
 
 // The learner step of one ready env, by one warp.  `ag` / `scratch` are this warp's shared memory.
+// stage 0: the whole step (independent policies).  Shared policy (one theta per handle):
+// stage 1 = evaluate under theta_t and accumulate the update into dtheta; stage 2 (after
+// theta += all-reduced dtheta) = Q(from, .) under theta_{t+1} for the next action selection.
 __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynParams& D, int env, AgentD& ag, unsigned char* scratch,
-                                               int lane, unsigned long long& steps_done, unsigned long long& sum_z) {
+                                               int lane, unsigned long long& steps_done, unsigned long long& sum_z, int stage) {
   const unsigned* s_rnd = rlm_rndseq_table;
   double* q_pre_a = (double*)(scratch + SCR_Q);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
@@ -346,15 +349,34 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
   double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
   unsigned long long bases[3];
-  if (ag.kind == 1) {
+  if (stage == 2) {
+    if (ag.kind == 0) {
+      if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+      __syncwarp();
+      double qa, qb;
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
+      if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+      ag.from_base0[lane] = mod_m(bases[0]);
+      if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+      steps_done++;
+    }
+  } else if (ag.kind == 1) {
     // end of warm-up: Q(null state, .) for the very first action selection
     double qa, qb;
     eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false);
     if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
-    if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; }
+    if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; ag.kind = 2; }
   } else {
     int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
     float* te = ptr.trace_e + (size_t)env * P.trace_cap;
+    if (stage == 1) {
+      // shared theta moved since the action was selected: UpdateTraces / UpdateWeights read Q(from, .)
+      // under the theta of NOW (agent.cpp:274,285 call getQ at update time), i.e. theta_t
+      double qa, qb;
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, ag.null_from != 0, vbuf, lane, qa, qb, bases, false);
+      if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+      __syncwarp();
+    }
     {  // Q(to, .) under the current theta
       double qa, qb;
       eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
@@ -368,6 +390,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       const float rate = (float)dec[0];
       const double scaled = dec[1];
       double* th = (dec[2] != 0.0) ? theta_b : theta_a;
+      if (stage == 1) th = (dec[2] != 0.0) ? ptr.dtheta + P.memory_size : ptr.dtheta;  // accumulate, apply after the all-reduce
       __syncwarp();
       int nz = trace_pass(ag, sset, tf, te, th, ag.cur_action, rate, scaled, lane);
       if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
@@ -389,17 +412,19 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
         ptr.record_count[env] = c + 1;
       }
     }
-    // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
-    if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
-    ag.from_base0[lane] = mod_m(bases[0]);
-    if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
-    __syncwarp();
-    {
-      double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true);
-      if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+    if (stage == 0) {
+      // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
+      if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+      ag.from_base0[lane] = mod_m(bases[0]);
+      if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+      __syncwarp();
+      {
+        double qa, qb;
+        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true);
+        if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+      }
+      steps_done++;
     }
-    steps_done++;
   }
   __syncwarp();
   {  // write the agent block back
@@ -412,7 +437,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
 
 // Tick-synchronous engine: one launch per tick after rlm_env_kernel.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rlm_agent_kernel(DevPtrs ptr, DynParams D, int tslot) {
+__global__ void __launch_bounds__(WARPS * 32) rlm_agent_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* wbase = smem + (size_t)warp * (AG_BYTES + P.scratch_bytes);
@@ -422,11 +447,29 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_agent_kernel(DevPtrs ptr, DynP
   unsigned long long steps_done = 0, sum_z = 0;
 #pragma unroll 1
   for (int idx = blockIdx.x * WARPS + warp; idx < n_ready; idx += gridDim.x * WARPS)
-    agent_process_env(ptr, D, ptr.ready[idx], ag, scratch, lane, steps_done, sum_z);
+    agent_process_env(ptr, D, ptr.ready[idx], ag, scratch, lane, steps_done, sum_z, stage);
   if (lane == 0 && (steps_done | sum_z)) {
     atomicAdd(&ptr.counters[1], steps_done);
     atomicAdd(&ptr.counters[2], sum_z);
   }
+}
+
+// theta += dtheta; dtheta = 0  (after the all-reduce of dtheta in shared-policy mode)
+__global__ void rlm_apply_dtheta_kernel(double* theta, double* dtheta, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 2;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+    double2 t = *(double2*)(theta + i), d = *(double2*)(dtheta + i);
+    t.x += d.x; t.y += d.y;
+    *(double2*)(theta + i) = t;
+    *(double2*)(dtheta + i) = make_double2(0.0, 0.0);
+  }
+}
+cudaError_t rlm_launch_apply_dtheta(double* theta, double* dtheta, long long n, int n_sms, cudaStream_t st) {
+  if (n & 1) return cudaErrorInvalidValue;
+  long long blocks = (n / 2 + 255) / 256;
+  if (blocks > (long long)n_sms * 8) blocks = (long long)n_sms * 8;
+  rlm_apply_dtheta_kernel<<<(int)blocks, 256, 0, st>>>(theta, dtheta, n);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,7 +518,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 4) rlm_run_kernel(DevPtrs ptr, Dy
       env = __shfl_sync(FULL, env, 0);
       if (env < 0) break;
       __threadfence();  // acquire: the env record published before the push
-      agent_process_env(ptr, D, env, ag, scratch, lane, steps_done, sum_z);
+      agent_process_env(ptr, D, env, ag, scratch, lane, steps_done, sum_z, 0);
       __threadfence();  // release: agent block, theta, traces
       if (lane == 0) *(volatile int*)(ptr.ag_done + env) = 1;
     }
@@ -590,7 +633,7 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
   return cudaGetLastError();
 }
 
-cudaError_t rlm_launch_agent(const DevPtrs& ptr, const DynParams& D, int n_envs, int scratch_bytes, int tslot, int n_sms, cudaStream_t st) {
+cudaError_t rlm_launch_agent(const DevPtrs& ptr, const DynParams& D, int n_envs, int scratch_bytes, int tslot, int n_sms, int stage, cudaStream_t st) {
   const int W = 8;
   size_t smem = rlm_agent_smem_bytes(W, scratch_bytes);
   static size_t attr_smem = 0;
@@ -602,7 +645,7 @@ cudaError_t rlm_launch_agent(const DevPtrs& ptr, const DynParams& D, int n_envs,
   int grid = (n_envs + W - 1) / W;      // worst case: every env is ready
   int cap = n_sms * 6;                  // beyond ~6 CTAs per SM the grid-stride loop takes over
   if (grid > cap) grid = cap;
-  rlm_agent_kernel<W><<<grid, W * 32, smem, st>>>(ptr, D, tslot);
+  rlm_agent_kernel<W><<<grid, W * 32, smem, st>>>(ptr, D, tslot, stage);
   return cudaGetLastError();
 }
 

@@ -16,7 +16,8 @@ EXPORTS = [
     "rlm_last_error", "rlm_abi_version", "rlm_config_default", "rlm_create", "rlm_destroy", "rlm_reset",
     "rlm_load_ticks", "rlm_run_ticks", "rlm_sync", "rlm_get_counters", "rlm_get_stats", "rlm_get_state",
     "rlm_get_reward", "rlm_get_actions", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
-    "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_apply_dtheta", "rlm_set_stream",
+    "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_shared_tick_accumulate", "rlm_apply_dtheta",
+    "rlm_set_stream",
     "rlm_flow_generate", "rlm_test_to_ticks", "rlm_test_to_price", "rlm_test_tiles", "rlm_test_order",
     "rlm_test_rolling_mean",
 ]
@@ -62,6 +63,7 @@ def load():
     L.rlm_read_records.argtypes = [C.c_void_p, C.c_int32, P(abi.StepRecord), C.c_int32, P(C.c_int32)]
     L.rlm_device_ptrs.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_void_p), P(C.c_int64)]
     L.rlm_apply_dtheta.argtypes = [C.c_void_p]
+    L.rlm_shared_tick_accumulate.argtypes = [C.c_void_p]
     L.rlm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.rlm_flow_generate.argtypes = [P(abi.FlowParams), C.c_int64, C.c_int64, C.c_int32, P(abi.TickMsg)]
     L.rlm_test_to_ticks.argtypes = [P(abi.Config), P(C.c_double), C.c_int32, P(C.c_int32)]
@@ -166,6 +168,27 @@ class BatchedMarket:
         out = (C.c_double * n)()
         check(self.L.rlm_read_theta(self.h, policy, table, out, n))
         return out
+
+    # ---- shared policy (cfg.shared_policy = 1), SURVEY.md section 8e
+    def shared_tick_accumulate(self):
+        check(self.L.rlm_shared_tick_accumulate(self.h))
+
+    def apply_dtheta(self):
+        check(self.L.rlm_apply_dtheta(self.h))
+
+    def dtheta_tensor(self):
+        """Zero-copy torch view of the device dtheta buffer (for torch.distributed.all_reduce)."""
+        import torch
+        theta, dtheta, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(self.L.rlm_device_ptrs(self.h, C.byref(theta), C.byref(dtheta), C.byref(n)))
+
+        class _Buf:
+            pass
+        buf = _Buf()
+        buf.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f8", "data": (dtheta.value, False), "version": 2}
+        t = torch.as_tensor(buf, device=torch.device("cuda", self.cfg.device))
+        t._rlm_keepalive = self
+        return t
 
     def records(self, env, cap=None):
         cap = self.cfg.record_cap if cap is None else cap

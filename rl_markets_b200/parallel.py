@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the collective.
+
+Independent policies (BASELINE.json configs 1, 2, 4) shard envs by rank and need NO data-path
+collective: rank r owns global envs [r*B, (r+1)*B) (config.env_index0), exactly like r*B..
+separate reference processes.
+
+Shared policy (config 3; reference analogue: threads sharing one rl::Agent*, src/main.cpp:196-206)
+has exactly one exchange per training tick: a SUM all-reduce of the accumulated weight update
+dtheta (memory_size fp64), after which every rank applies theta += dtheta to its replica.
+"""
+
+
+def shard(n_envs_total, rank, world):
+    """Contiguous block partition: (first global env index, number of local envs)."""
+    base, rem = divmod(n_envs_total, world)
+    n = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n
+
+
+def shared_policy_tick(accumulate, dtheta, apply, dist=None):
+    """One training tick of a policy shared across ranks.
+
+    accumulate(): env tick + learner steps under theta_t, update summed into `dtheta` (a tensor view)
+    apply():      theta += dtheta; dtheta = 0; next actions under theta_{t+1}
+    dist:         torch.distributed (initialised) or None for a single process
+    """
+    accumulate()
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(dtheta, op=dist.ReduceOp.SUM)
+    apply()
+
+
+def run_shared_policy(market, n_ticks, dist=None):
+    """market: rl_markets_b200.lib.BatchedMarket created with shared_policy=True."""
+    dth = market.dtheta_tensor() if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+    if dth is None:
+        market.run_ticks(n_ticks)
+        return
+    import torch
+    for _ in range(n_ticks):
+        market.shared_tick_accumulate()
+        # the library runs on its own stream: order the collective after it
+        market.sync()
+        dist.all_reduce(dth, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().synchronize()
+        market.apply_dtheta()
