@@ -26,9 +26,13 @@ sys.path.insert(0, ROOT)
 TICKS_PER_LAUNCH = 64
 WORKLOADS = {
     # BASELINE.json configs[1]: 4096 parallel LOBs, Q-learning tile coding, synthetic Poisson flow, 1xB200
-    "C1": dict(envs=4096, algo="q_learn", memory_size=65536),
-    # configs[2]: 65536 LOBs, SARSA(lambda)
-    "C2": dict(envs=65536, algo="sarsa", memory_size=16384),
+    "C1": dict(envs=4096, algo="q_learn", memory_size=65536, shared=False),
+    # configs[2]: 65536 LOBs, SARSA(lambda) with eligibility traces, 1xB200
+    "C2": dict(envs=65536, algo="sarsa", memory_size=16384, shared=False),
+    # configs[3]: 262144 LOBs over 8 GPUs (32768 per GPU), shared policy, per-tick NCCL all-reduce of dtheta
+    "C3": dict(envs=32768, algo="q_learn", memory_size=1 << 22, shared=True),
+    # configs[4]: 1M LOBs over 8 GPUs (131072 per GPU), independent policies, no collective
+    "C4": dict(envs=131072, algo="q_learn", memory_size=4096, shared=False),
 }
 
 
@@ -83,7 +87,8 @@ def make_cfg(workload, n_envs, env_index0, source, args):
     y = config.example_dict(**{"learning.memory_size": args.memory_size or w["memory_size"],
                                "learning.algorithm": args.algo or w["algo"]})
     # dt_ms = 1: 27e6 ticks per synthetic trading day, so no env reaches the close inside a bench run
-    cfg = config.from_dict(y, n_envs=n_envs, env_index0=env_index0, source=source, flow_seed=2024, dt_ms=1)
+    cfg = config.from_dict(y, n_envs=n_envs, env_index0=env_index0, source=source, flow_seed=2024, dt_ms=1,
+                           shared_policy=bool(w.get("shared")))
     return y, cfg
 
 
@@ -107,6 +112,18 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     m.set_stream(stream.cuda_stream)
     ticks = args.ticks
+    shared = bool(w.get("shared"))
+    from rl_markets_b200 import parallel
+    dist_mod = None
+    if world > 1:
+        import torch.distributed as dist_mod  # noqa: F811
+
+    def run_chunk():
+        if shared and world > 1:
+            with torch.cuda.stream(stream):
+                parallel.run_shared_policy(m, ticks, dist_mod)
+        else:
+            m.run_ticks(ticks)
 
     def barrier():
         torch.cuda.synchronize()
@@ -117,7 +134,7 @@ def run_ours(args):
 
     # ---- device-resident run (inputs = generator state, theta, traces: all in HBM)
     for _ in range(max(args.warmup, 3)):
-        m.run_ticks(ticks)
+        run_chunk()
     m.sync()
     c0 = m.counters()
     sampler = ClockSampler(local)
@@ -127,7 +144,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         evs[0].record(stream)
         for i in range(args.steps):
-            m.run_ticks(ticks)
+            run_chunk()
             evs[i + 1].record(stream)
     barrier()
     sampler.stop_flag = True
@@ -138,11 +155,28 @@ def run_ours(args):
     steps_done = c1.steps - c0.steps
     ticks_done = c1.ticks - c0.ticks
     z_sum = c1.sum_traces - c0.sum_traces
+    launches_timed = c1.kernel_launches - c0.kernel_launches
+
+    # ---- per-kernel durations (CUDA events around every launch, on the launching stream): a separate pass,
+    # because the events serialise host launch and device execution; not used for `value`
+    kt = None
+    if not shared:
+        m.set_profiling(True)
+        cp0 = m.counters()
+        for _ in range(min(args.steps, 5)):
+            m.run_ticks(ticks)
+        m.sync()
+        cp1 = m.counters()
+        kt = m.kernel_times()
+        kt["steps"] = cp1.steps - cp0.steps
+        kt["ticks"] = cp1.ticks - cp0.ticks
+        kt["sum_traces"] = cp1.sum_traces - cp0.sum_traces
+        m.set_profiling(False)
 
     # ---- end to end through the C ABI with HOST buffers: every launch uploads its tick messages from
     # pinned host memory (rlm_load_ticks) and reads the per-env rewards back (rlm_get_reward)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not shared:
         y2, cfg2 = make_cfg(args.workload, B, rank * B, abi.SOURCE_STREAM, args)
         cfg2.device = local
         m2 = lib.BatchedMarket(cfg2)
@@ -207,10 +241,27 @@ def run_ours(args):
         b_step = algorithmic_bytes_per_step(k_bar, z_bar, is_dq)
         value = steps_all / (total_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = rlm_tick_kernel (the only kernel in the timed region): per-launch numbers, rank 0
-        avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
-        launch_steps = steps_done / args.steps
-        achieved = launch_steps * b_step / (avg_launch_ms * 1e-3) / 1e9
+        # dominant kernel = rlm_agent_kernel (one launch per market tick); its algorithmic bytes are the agent
+        # share of B_step: theta gathers + trace list (13824 + 28 Z per env step), SURVEY.md section 8d
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_summary.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("agent_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+        if kt and kt["agent_launches"]:
+            avg_launch_ms = kt["agent_ms"] / kt["agent_launches"]
+            launch_steps = kt["steps"] / kt["agent_launches"]
+            z_k = kt["sum_traces"] / max(kt["steps"], 1)
+            b_agent = (27648.0 if is_dq else 13824.0) + 28.0 * z_k
+            achieved = launch_steps * b_agent / (avg_launch_ms * 1e-3) / 1e9
+            env_avg_ms = kt["env_ms"] / max(kt["env_launches"], 1)
+        else:
+            avg_launch_ms = total_ms / max(launches_timed, 1)
+            launch_steps = steps_done / max(launches_timed, 1)
+            b_agent = b_step
+            achieved = steps_done * b_step / (total_ms * 1e-3) / 1e9
+            env_avg_ms = None
         line = {
             "metric": "env steps/sec (batched LOBs)", "value": value, "unit": "env_steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -218,15 +269,20 @@ def run_ours(args):
             "config": {"workload": "%s: %d parallel LOBs per GPU, %s + tile coding (32 tilings, memory_size %d per env), "
                                    "synthetic Poisson order flow (in-kernel generator), %d ticks per launch"
                                    % (args.workload, B, args.algo or w["algo"], args.memory_size or w["memory_size"], ticks),
-                       "envs_per_gpu": B, "ticks_per_launch": ticks, "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar,
+                       "envs_per_gpu": B, "ticks_per_bench_step": ticks, "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar,
+                       "policy": "shared theta, one SUM all-reduce of dtheta per tick" if shared else "independent theta per env, no collective",
                        "l2": "working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * (args.memory_size or w["memory_size"]) * 8 / 1e9),
                        "ticks_per_s": ticks_all / (total_ms * 1e-3)},
-            "gpu_launches": args.steps,
+            "gpu_launches": int(launches_timed),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "rlm_tick_kernel",
-                         "algorithmic_bytes_per_env_step": b_step, "env_steps_per_launch": launch_steps,
-                         "avg_launch_ms": avg_launch_ms},
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "rlm_agent_kernel",
+                         "algorithmic_bytes_per_env_step_agent_kernel": b_agent,
+                         "algorithmic_bytes_per_env_step_whole_path": b_step,
+                         "whole_path_achieved_GBps": steps_all * b_step / (total_ms * 1e-3) / 1e9 / max(world, 1),
+                         "env_steps_per_launch": launch_steps, "avg_launch_ms": avg_launch_ms,
+                         "env_kernel_avg_launch_ms": env_avg_ms,
+                         "timing": "CUDA events around every kernel launch on the launching stream, separate pass"},
         }
         if e2e:
             line["e2e"] = {"value": e2e["steps"] / e2e["seconds"], "unit": "env_steps/s",

@@ -195,6 +195,9 @@ int rlm_device_ptrs(rlm_handle h, void** theta, void** dtheta, int64_t* n_double
  * On one GPU rlm_run_ticks does the same without the collective. */
 int rlm_shared_tick_accumulate(rlm_handle h);
 int rlm_apply_dtheta(rlm_handle h);
+/* measurement hooks (bench.py): CUDA-event durations of the env-tick and agent kernels, summed over launches */
+int rlm_set_profiling(rlm_handle h, int32_t on);
+int rlm_get_kernel_times(rlm_handle h, double* env_ms, double* agent_ms, int64_t* env_launches, int64_t* agent_launches);
 /* run on a caller-provided CUDA stream (cudaStream_t as void*); 0 = the handle's own stream */
 int rlm_set_stream(rlm_handle h, void* cuda_stream);
 

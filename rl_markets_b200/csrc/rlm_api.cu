@@ -41,6 +41,11 @@ struct rlm_handle_s {
   unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
   DynParams shared_dyn;
   bool in_run = false;
+  // optional per-kernel timing (bench.py roofline leg): CUDA events around every launch of a run call
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;
+  double prof_env_ms = 0, prof_agent_ms = 0;
+  long long prof_env_launches = 0, prof_agent_launches = 0;
   int ready_cap = 0;  // ticks per run call the ready counters can hold
   int n_policies = 1;
   size_t env_bytes = 0;
@@ -299,6 +304,7 @@ int rlm_destroy(rlm_handle h) {
   cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters); cudaFree(h->d_stream);
   cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count);
   cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
+  for (auto e : h->ev) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (g_params_owner == h) g_params_owner = nullptr;
   delete h;
@@ -387,12 +393,28 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
   while (done < n_ticks) {
     const int chunk = std::min(n_ticks - done, h->ready_cap);
     CK(cudaMemsetAsync(h->ptr.ready_count, 0, (size_t)chunk * 4, h->stream));
+    if (h->profile) {
+      while ((int)h->ev.size() < 3 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev.push_back(e); }
+    }
     for (int t = 0; t < chunk; ++t) {
       DynParams dt = d;
       dt.stream_off = d.stream_off + done;
+      if (h->profile) CK(cudaEventRecord(h->ev[3 * t], h->stream));
       CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->stream));
+      if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 1], h->stream));
       CK(rlm_launch_agent(h->ptr, dt, h->cfg.n_envs, h->hp.scratch_bytes, t, h->n_sms, 0, h->stream));
+      if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 2], h->stream));
       h->launches += 2;
+    }
+    if (h->profile) {
+      CK(cudaStreamSynchronize(h->stream));
+      for (int t = 0; t < chunk; ++t) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, h->ev[3 * t], h->ev[3 * t + 1]));
+        CK(cudaEventElapsedTime(&b, h->ev[3 * t + 1], h->ev[3 * t + 2]));
+        h->prof_env_ms += a; h->prof_agent_ms += b;
+        h->prof_env_launches++; h->prof_agent_launches++;
+      }
     }
     done += chunk;
   }
@@ -588,6 +610,22 @@ int rlm_apply_dtheta(rlm_handle h) {
   CK(rlm_launch_agent(h->ptr, h->shared_dyn, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 2, h->stream));
   CK(rlm_launch_env(h->ptr, h->shared_dyn, h->cfg.n_envs, 0, 1, h->stream));
   h->launches += 3;
+  return RLM_OK;
+}
+
+// bench instrumentation: CUDA-event time of every env / agent kernel launch of the tick-synchronous engine
+int rlm_set_profiling(rlm_handle h, int32_t on) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  h->profile = on != 0;
+  h->prof_env_ms = h->prof_agent_ms = 0; h->prof_env_launches = h->prof_agent_launches = 0;
+  return RLM_OK;
+}
+int rlm_get_kernel_times(rlm_handle h, double* env_ms, double* agent_ms, int64_t* env_launches, int64_t* agent_launches) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  if (env_ms) *env_ms = h->prof_env_ms;
+  if (agent_ms) *agent_ms = h->prof_agent_ms;
+  if (env_launches) *env_launches = h->prof_env_launches;
+  if (agent_launches) *agent_launches = h->prof_agent_launches;
   return RLM_OK;
 }
 

@@ -17,7 +17,7 @@ EXPORTS = [
     "rlm_load_ticks", "rlm_run_ticks", "rlm_sync", "rlm_get_counters", "rlm_get_stats", "rlm_get_state",
     "rlm_get_reward", "rlm_get_actions", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
     "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_shared_tick_accumulate", "rlm_apply_dtheta",
-    "rlm_set_stream",
+    "rlm_set_stream", "rlm_set_profiling", "rlm_get_kernel_times",
     "rlm_flow_generate", "rlm_test_to_ticks", "rlm_test_to_price", "rlm_test_tiles", "rlm_test_order",
     "rlm_test_rolling_mean",
 ]
@@ -65,6 +65,8 @@ def load():
     L.rlm_apply_dtheta.argtypes = [C.c_void_p]
     L.rlm_shared_tick_accumulate.argtypes = [C.c_void_p]
     L.rlm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.rlm_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+    L.rlm_get_kernel_times.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int64)]
     L.rlm_flow_generate.argtypes = [P(abi.FlowParams), C.c_int64, C.c_int64, C.c_int32, P(abi.TickMsg)]
     L.rlm_test_to_ticks.argtypes = [P(abi.Config), P(C.c_double), C.c_int32, P(C.c_int32)]
     L.rlm_test_to_price.argtypes = [P(abi.Config), P(C.c_int32), C.c_int32, P(C.c_double)]
@@ -168,6 +170,14 @@ class BatchedMarket:
         out = (C.c_double * n)()
         check(self.L.rlm_read_theta(self.h, policy, table, out, n))
         return out
+
+    def set_profiling(self, on):
+        check(self.L.rlm_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        a, b, na, nb = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+        check(self.L.rlm_get_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(na), C.byref(nb)))
+        return {"env_ms": a.value, "agent_ms": b.value, "env_launches": na.value, "agent_launches": nb.value}
 
     # ---- shared policy (cfg.shared_policy = 1), SURVEY.md section 8e
     def shared_tick_accumulate(self):
