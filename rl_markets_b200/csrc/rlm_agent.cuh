@@ -150,19 +150,27 @@ __device__ __forceinline__ double seg_sum(double acc, double w, const double* r)
 // 32..64 dependent multiply-adds of the previous one.
 struct QGather { double a[RLM_MAX_ACTIONS]; double b[RLM_MAX_ACTIONS]; };
 
+// idx: this warp's [27][32] tile-index cache in shared memory (row g*9+a, column lane).  The first
+// evaluation of a step fills it, the second one (same state, updated theta) just reads it back.
 __device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
-                                        bool null_state, int g, int lane, unsigned long long* bases, bool reuse, QGather& out) {
+                                        bool null_state, int g, int lane, unsigned long long* bases, bool reuse, int* idx,
+                                        QGather& out) {
   const int A = P.n_actions;
-  const float* gv = (g == 1) ? vars + 3 : vars;
-  const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
-  unsigned long long base = 0ull;
-  if (!null_state) {
-    if (reuse) base = bases[g];
-    else { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
-  }
   int f[RLM_MAX_ACTIONS];
+  if (reuse) {
 #pragma unroll
-  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A) ? idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane] : 0;
+  } else {
+    const float* gv = (g == 1) ? vars + 3 : vars;
+    const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
+    unsigned long long base = 0ull;
+    if (!null_state) { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+      f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
+      if (a < A) idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane] = f[a];
+    }
+  }
 #pragma unroll
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.a[a] = (a < A) ? __ldcg(th_a + f[a]) : 0.0;  // L2-coherent: theta is rewritten by trace_pass, possibly from another SM
   if (th_b) {
@@ -173,16 +181,16 @@ __device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a,
 
 __device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
                        bool null_state, double* vbuf, int lane, double& qa_out, double& qb_out,
-                       unsigned long long* bases, bool reuse) {
+                       unsigned long long* bases, bool reuse, int* idx) {
   const int A = P.n_actions;
   double qa = 0.0, qb = 0.0;
   double* va = vbuf;
   double* vb = vbuf + RLM_MAX_ACTIONS * VROW;
   QGather cur, nxt;
-  q_issue(rnd, th_a, th_b, vars, n, null_state, 0, lane, bases, reuse, cur);
+  q_issue(rnd, th_a, th_b, vars, n, null_state, 0, lane, bases, reuse, idx, cur);
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    if (g < 2) q_issue(rnd, th_a, th_b, vars, n, null_state, g + 1, lane, bases, reuse, nxt);
+    if (g < 2) q_issue(rnd, th_a, th_b, vars, n, null_state, g + 1, lane, bases, reuse, idx, nxt);
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
       if (a < A) {

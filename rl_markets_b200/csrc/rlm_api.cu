@@ -38,6 +38,7 @@ struct rlm_handle_s {
   int n_sms = 148;
   int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent (rlm_run_kernel)
   int n_agent_ctas = 0;  // persistent engine: CTAs in the agent role
+  int env_variant = 0;   // env tick kernel: 0 = warp per env, 1 = thread per env
   unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
   DynParams shared_dyn;
   bool in_run = false;
@@ -287,6 +288,9 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     h->n_agent_ctas = std::max(1, std::min(want, cap));
     if (const char* s = getenv("RLM_AGENT_CTAS")) { int v = atoi(s); if (v > 0 && v < resident) h->n_agent_ctas = v; }
     if (const char* s = getenv("RLM_ENGINE")) h->engine = (s[0] == 'p') ? 0 : 1;
+    // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
+    h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
+    if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
@@ -400,7 +404,7 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
       DynParams dt = d;
       dt.stream_off = d.stream_off + done;
       if (h->profile) CK(cudaEventRecord(h->ev[3 * t], h->stream));
-      CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->stream));
+      CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->env_variant, h->stream));
       if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 1], h->stream));
       CK(rlm_launch_agent(h->ptr, dt, h->cfg.n_envs, h->hp.scratch_bytes, t, h->n_sms, 0, h->stream));
       if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 2], h->stream));
@@ -418,7 +422,7 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     }
     done += chunk;
   }
-  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 1, h->stream));
+  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 1, h->env_variant, h->stream));
   h->launches++;
   return RLM_OK;
 }
@@ -588,7 +592,7 @@ int rlm_shared_tick_accumulate(rlm_handle h) {
     h->stream_cursor += 1;
   }
   CK(cudaMemsetAsync(h->ptr.ready_count, 0, 4, h->stream));
-  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 0, h->stream));
+  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 0, h->env_variant, h->stream));
   CK(rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 1, h->stream));
   h->launches += 2;
   h->shared_dyn = d;
@@ -608,7 +612,7 @@ int rlm_apply_dtheta(rlm_handle h) {
   if (h->hp.is_double) CK(rlm_launch_apply_dtheta(h->ptr.theta_b, h->ptr.dtheta + h->cfg.memory_size, h->cfg.memory_size, h->n_sms, h->stream));
   (void)n;
   CK(rlm_launch_agent(h->ptr, h->shared_dyn, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 2, h->stream));
-  CK(rlm_launch_env(h->ptr, h->shared_dyn, h->cfg.n_envs, 0, 1, h->stream));
+  CK(rlm_launch_env(h->ptr, h->shared_dyn, h->cfg.n_envs, 0, 1, h->env_variant, h->stream));
   h->launches += 3;
   return RLM_OK;
 }

@@ -28,7 +28,8 @@
 // per-warp scratch: [q_pre_a, q_pre_b: 18 doubles][small set: 64 ints][vbuf: (1|2) * A_max * VROW doubles]
 #define SCR_Q 0
 #define SCR_SS (SCR_Q + 8 * 2 * RLM_MAX_ACTIONS)
-#define SCR_VBUF (SCR_SS + 4 * SS_SLOTS)
+#define SCR_IDX (SCR_SS + 4 * SS_SLOTS)                    // int idx[27][32]: tile indices of the to-state
+#define SCR_VBUF (SCR_IDX + 4 * 3 * RLM_MAX_ACTIONS * 32)
 #define AG_BYTES ((sizeof(AgentD) + 15) & ~(size_t)15)
 size_t rlm_scratch_bytes(int is_double) {
   return ((size_t)SCR_VBUF + (size_t)(is_double ? 2 : 1) * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15;
@@ -283,6 +284,124 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Env tick, one WARP per env (the latency-oriented variant; default).  The env record is staged in
+// shared memory with coalesced 16-byte copies; lane 0 runs the scalar market logic, lanes 0..9 own one
+// rolling window each (ring loads are issued first so their HBM/L2 round trips overlap the book logic),
+// lanes 0..7 each evaluate one state variable at a step end.  No env waits for another one: a warp whose
+// env needs the learner step just appends it to the ready list.
+#define ENVW_WARPS 8
+__global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr, DynParams D, int tslot, int only_begin) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env = blockIdx.x * ENVW_WARPS + warp;
+  if (env >= P.n_envs) return;
+  const int hdr_bytes = (int)((sizeof(EnvHdr) + 15) & ~(size_t)15);
+  unsigned char* wbase = smem + (size_t)warp * (hdr_bytes + 128 + 8 * 2 * RLM_NWIN + 16);
+  EnvHdr& e = *(EnvHdr*)wbase;
+  rlm_tick_msg& msg = *(rlm_tick_msg*)(wbase + hdr_bytes);
+  double* pushv = (double*)(wbase + hdr_bytes + 128);
+  double* oldv = pushv + RLM_NWIN;
+  int* flag = (int*)(oldv + RLM_NWIN);
+  EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
+  double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
+  {
+    const int ph = g->phase, nb = g->ag.need_begin;  // uniform: skip idle envs without staging them
+    if (ph == PH_DONE || (only_begin && !nb)) return;
+    const int4* src = (const int4*)g;
+    int4* dst = (int4*)&e;
+    for (int i = lane; i < hdr_bytes / 16; i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  int ready = -1;
+  unsigned ticked = 0;
+  if (e.ag.need_begin) {
+    if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
+    __syncwarp();
+  }
+  if (!only_begin && e.phase != PH_DONE) {
+    bool have = true;
+    if (P.source == RLM_SOURCE_GENERATOR) {
+      if (lane == 0) flow_next_dev(&e.flow, &msg);
+    } else {
+      const int pos = D.stream_off + tslot;
+      if (pos >= D.stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; have = false; }
+      else ((unsigned*)&msg)[lane] = __ldg((const unsigned*)(ptr.stream + ((size_t)pos * P.n_envs + env)) + lane);
+    }
+    if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);  // issued early, consumed after the book logic
+    __syncwarp();
+    const int phase = e.phase;
+    if (have && phase == PH_PREOPEN) {  // intraday.cpp:111-116
+      if (lane == 0) {
+        msg.n_tx = 0;
+        update_book_profiles(e, msg);
+        if (market_is_open(e)) e.phase = PH_WARMUP;
+      }
+    } else if (have) {
+      ticked = 1;
+      if (lane == 0) {
+        if (phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
+        next_state_scalar(e, msg, pushv);       // Intraday::NextState
+      }
+      __syncwarp();
+      if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
+      __syncwarp();
+      if (lane == 0) {
+        int r = -1;
+        e.tp_val = e.w_mean[W_TP];
+        if (phase == PH_WARMUP) {  // intraday.cpp:118-135
+          bool full = true;
+          for (int w = 0; w < 8; ++w) full = full && (e.w_count[w] == P.win_size[w]);
+          if (full) {
+            place_orders(e, 1, 1);
+            e.phase = PH_RUN;
+            e.ag.kind = 1;  // serial.cpp:24-25,55-60: the first from-state is the never-populated State
+            r = 1;
+          }
+        } else {
+          // tail of one iteration of performAction's do-while (base.cpp:292-305)
+          double mpm = m_midprice(e) - m_last_midprice(e);
+          e.pnl_step += (double)e.position * mpm;
+          e.momentum_pnl_step += (double)e.position * mpm;
+          e.agg_r += get_reward(e);
+          e.agg_pnl += e.pnl_step;
+          e.agg_mpm += mpm;
+          if (!(!is_terminal(e) && fabs(e.agg_mpm) < 1e-5)) {
+            e.pnl_step = e.agg_pnl;  // base.cpp:317-331
+            pushv[W_PNLUP] = fmax(0.0, e.pnl_step);
+            pushv[W_PNLDN] = fabs(fmin(0.0, e.pnl_step));
+            e.ep_reward += e.agg_r;
+            e.ep_bandh += e.agg_mpm;
+            r = 0;
+          }
+        }
+        *flag = r;
+      }
+      __syncwarp();
+      ready = *flag;
+      if (ready == 0) {
+        if (lane == W_PNLUP || lane == W_PNLDN) window_push(e, ring, lane, pushv[lane], oldv[lane]);
+        __syncwarp();
+        // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
+        if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
+        if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
+      }
+    }
+  }
+  __syncwarp();
+  {
+    int4* dst = (int4*)g;
+    const int4* src = (const int4*)&e;
+    for (int i = lane; i < hdr_bytes / 16; i += 32) dst[i] = src[i];
+  }
+  if (lane == 0) {
+    if (ready >= 0) ptr.ready[atomicAdd(&ptr.ready_count[tslot], 1)] = env;
+    if (ticked) atomicAdd(&ptr.counters[0], 1ull);
+    const unsigned errs = (unsigned)(e.err | e.ag.err);
+    if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
+  }
+}
+
 // TD error + trace decision of Agent::HandleTransition (agent.cpp:86-101); lane 0.
 // out[0] = trace decay rate, out[1] = alpha*delta/N_TILINGS, out[2] = table (0 = A, 1 = B)
 __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, const double* q_pre_b, unsigned long long* mt_pol,
@@ -335,6 +454,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   double* q_pre_a = (double*)(scratch + SCR_Q);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   int* sset = (int*)(scratch + SCR_SS);
+  int* idxc = (int*)(scratch + SCR_IDX);
   double* vbuf = (double*)(scratch + SCR_VBUF);
   double* dec = vbuf;  // 3 doubles handed from lane 0 to the warp (vbuf is free between the evaluations)
   const int A = P.n_actions;
@@ -354,7 +474,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
       __syncwarp();
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc);
       if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       ag.from_base0[lane] = mod_m(bases[0]);
       if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
@@ -363,7 +483,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   } else if (ag.kind == 1) {
     // end of warm-up: Q(null state, .) for the very first action selection
     double qa, qb;
-    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false);
+    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false, idxc);
     if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
     if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; ag.kind = 2; }
   } else {
@@ -373,13 +493,13 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       // shared theta moved since the action was selected: UpdateTraces / UpdateWeights read Q(from, .)
       // under the theta of NOW (agent.cpp:274,285 call getQ at update time), i.e. theta_t
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, ag.null_from != 0, vbuf, lane, qa, qb, bases, false);
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, ag.null_from != 0, vbuf, lane, qa, qb, bases, false, idxc);
       if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       __syncwarp();
     }
     {  // Q(to, .) under the current theta
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false);
+      eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc);
       if (lane < A) { q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
     }
     __syncwarp();
@@ -420,7 +540,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       __syncwarp();
       {
         double qa, qb;
-        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true);
+        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true, idxc);
         if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       }
       steps_done++;
@@ -627,9 +747,21 @@ int rlm_run_max_resident_ctas(int scratch_bytes, int n_sms) {
 }
 
 // ---------------------------------------------------------------------------------------------
-cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, int only_begin, cudaStream_t st) {
-  const int T = 32;  // one warp per CTA: at small batches every SM gets work
-  rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
+cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, int only_begin, int variant, cudaStream_t st) {
+  if (variant == 1) {  // one thread per env (SIMT over envs)
+    const int T = 32;
+    rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
+    return cudaGetLastError();
+  }
+  const size_t per_warp = ((sizeof(EnvHdr) + 15) & ~(size_t)15) + 128 + 8 * 2 * RLM_NWIN + 16;
+  const size_t smem = ENVW_WARPS * per_warp;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  rlm_env_kernel_w<<<(n_envs + ENVW_WARPS - 1) / ENVW_WARPS, ENVW_WARPS * 32, smem, st>>>(ptr, D, tslot, only_begin);
   return cudaGetLastError();
 }
 
