@@ -271,7 +271,8 @@ def run_ours(args):
                                    % (args.workload, B, args.algo or w["algo"], args.memory_size or w["memory_size"], ticks),
                        "envs_per_gpu": B, "ticks_per_bench_step": ticks, "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar,
                        "policy": "shared theta, one SUM all-reduce of dtheta per tick" if shared else "independent theta per env, no collective",
-                       "l2": "working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * (args.memory_size or w["memory_size"]) * 8 / 1e9),
+                       "l2": ("working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * (args.memory_size or w["memory_size"]) * 8 / 1e9))
+                             if not shared else ("shared theta %.0f MB (L2-resident) + %.1f GB of env records, traces and generator state" % ((args.memory_size or w["memory_size"]) * 8 / 1e6, B * 8.0e3 / 1e9)),
                        "ticks_per_s": ticks_all / (total_ms * 1e-3)},
             "gpu_launches": int(launches_timed),
             "clocks": sampler.summary(),
