@@ -157,18 +157,21 @@ __device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a,
                                         QGather& out) {
   const int A = P.n_actions;
   int f[RLM_MAX_ACTIONS];
-  if (reuse) {
+  if (reuse && idx) {
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A) ? idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane] : 0;
   } else {
     const float* gv = (g == 1) ? vars + 3 : vars;
     const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
     unsigned long long base = 0ull;
-    if (!null_state) { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
+    if (!null_state) {
+      if (reuse) base = bases[g];  // no index cache (fused kernel): reuse at least the partial hash sums
+      else { base = tile_base_sum(rnd, gv, nf, lane); bases[g] = base; }
+    }
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
       f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
-      if (a < A) idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane] = f[a];
+      if (a < A && idx) idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane] = f[a];
     }
   }
 #pragma unroll

@@ -36,7 +36,7 @@ struct rlm_handle_s {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   int n_sms = 148;
-  int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent (rlm_run_kernel)
+  int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent queue (rlm_run_kernel), 2 fused (warp per env)
   int n_agent_ctas = 0;  // persistent engine: CTAs in the agent role
   int env_variant = 0;   // env tick kernel: 0 = warp per env, 1 = thread per env
   unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
@@ -287,7 +287,7 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     int cap = resident - std::min(n_env_ctas, std::max(resident / 4, 1));
     h->n_agent_ctas = std::max(1, std::min(want, cap));
     if (const char* s = getenv("RLM_AGENT_CTAS")) { int v = atoi(s); if (v > 0 && v < resident) h->n_agent_ctas = v; }
-    if (const char* s = getenv("RLM_ENGINE")) h->engine = (s[0] == 'p') ? 0 : 1;
+    if (const char* s = getenv("RLM_ENGINE")) h->engine = (s[0] == 'p') ? 0 : ((s[0] == 'f') ? 2 : 1);
     // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
     h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
     if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
@@ -381,6 +381,11 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     }
     h->dyn = keep;
     h->in_run = false;
+    return RLM_OK;
+  }
+  if (h->engine == 2) {
+    CK(rlm_launch_fused(h->ptr, d, h->cfg.n_envs, h->hp.is_double, h->stream));
+    h->launches += 1;
     return RLM_OK;
   }
   if (h->engine == 0) {

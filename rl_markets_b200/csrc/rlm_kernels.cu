@@ -448,18 +448,28 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
 // stage 0: the whole step (independent policies).  Shared policy (one theta per handle):
 // stage 1 = evaluate under theta_t and accumulate the update into dtheta; stage 2 (after
 // theta += all-reduced dtheta) = Q(from, .) under theta_{t+1} for the next action selection.
-__device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynParams& D, int env, AgentD& ag, unsigned char* scratch,
-                                               int lane, unsigned long long& steps_done, unsigned long long& sum_z, int stage) {
+struct AgentScratch { double* q_pre; int* sset; int* idx; double* vbuf; };
+__device__ __forceinline__ AgentScratch std_scratch(unsigned char* scratch) {
+  AgentScratch s;
+  s.q_pre = (double*)(scratch + SCR_Q); s.sset = (int*)(scratch + SCR_SS); s.idx = (int*)(scratch + SCR_IDX);
+  s.vbuf = (double*)(scratch + SCR_VBUF);
+  return s;
+}
+// `resident` != nullptr: the env record (and `ag` = resident->ag) already lives in this warp's shared
+// memory (fused kernel): nothing is staged or written back here.
+__device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynParams& D, int env, AgentD& ag, AgentScratch sc,
+                                               int lane, unsigned long long& steps_done, unsigned long long& sum_z, int stage,
+                                               const EnvHdr* resident) {
   const unsigned* s_rnd = rlm_rndseq_table;
-  double* q_pre_a = (double*)(scratch + SCR_Q);
+  double* q_pre_a = sc.q_pre;
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
-  int* sset = (int*)(scratch + SCR_SS);
-  int* idxc = (int*)(scratch + SCR_IDX);
-  double* vbuf = (double*)(scratch + SCR_VBUF);
+  int* sset = sc.sset;
+  int* idxc = sc.idx;
+  double* vbuf = sc.vbuf;
   double* dec = vbuf;  // 3 doubles handed from lane 0 to the warp (vbuf is free between the evaluations)
   const int A = P.n_actions;
   EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
-  {  // stage the agent block: coalesced 16-byte L2 loads (the block was written by another SM)
+  if (!resident) {  // stage the agent block: coalesced 16-byte L2 loads (the block was written by another SM)
     const int4* src = (const int4*)&g->ag;
     int4* dst = (int4*)&ag;
     for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) dst[i] = __ldcg(src + i);
@@ -521,14 +531,17 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
     if (env < P.record_envs) {  // parity record: the env part is read back from HBM (published by the env thread)
       unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
       if (lane == 0) {
-        EnvHdr tmp;
-        {
-          const int4* src = (const int4*)g;
-          int4* dst = (int4*)&tmp;
-          for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
-        }
         int c = ptr.record_count[env];
-        if (c < P.record_cap) fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h);
+        if (c < P.record_cap) {
+          if (resident) fill_record(&ptr.records[(size_t)env * P.record_cap + c], *resident, ag, h);
+          else {
+            EnvHdr tmp;
+            const int4* src = (const int4*)g;
+            int4* dst = (int4*)&tmp;
+            for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
+            fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h);
+          }
+        }
         ptr.record_count[env] = c + 1;
       }
     }
@@ -547,7 +560,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
     }
   }
   __syncwarp();
-  {  // write the agent block back
+  if (!resident) {  // write the agent block back
     int4* dst = (int4*)&g->ag;
     const int4* src = (const int4*)&ag;
     for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) __stcg(dst + i, src[i]);
@@ -567,7 +580,7 @@ __global__ void __launch_bounds__(WARPS * 32) rlm_agent_kernel(DevPtrs ptr, DynP
   unsigned long long steps_done = 0, sum_z = 0;
 #pragma unroll 1
   for (int idx = blockIdx.x * WARPS + warp; idx < n_ready; idx += gridDim.x * WARPS)
-    agent_process_env(ptr, D, ptr.ready[idx], ag, scratch, lane, steps_done, sum_z, stage);
+    agent_process_env(ptr, D, ptr.ready[idx], ag, std_scratch(scratch), lane, steps_done, sum_z, stage, nullptr);
   if (lane == 0 && (steps_done | sum_z)) {
     atomicAdd(&ptr.counters[1], steps_done);
     atomicAdd(&ptr.counters[2], sum_z);
@@ -589,6 +602,146 @@ cudaError_t rlm_launch_apply_dtheta(double* theta, double* dtheta, long long n, 
   long long blocks = (n / 2 + 255) / 256;
   if (blocks > (long long)n_sms * 8) blocks = (long long)n_sms * 8;
   rlm_apply_dtheta_kernel<<<(int)blocks, 256, 0, st>>>(theta, dtheta, n);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused engine (default for independent policies): ONE launch, one warp per env for all `n_ticks` ticks.
+// The env record stays in shared memory for the whole launch; the warp runs the tick (lane 0 scalar +
+// lane-parallel windows / state variables) and, whenever its env's midprice has moved, the learner step
+// inline -- so envs never wait for each other and the theta gathers of some warps overlap the book
+// logic of others.  14 warps per CTA, 2 CTAs per SM: 4096 envs are exactly one resident wave on 148 SMs.
+#define FUSED_WARPS 14
+#define FU_MSG 0
+#define FU_PUSH (FU_MSG + 128)
+#define FU_FLAG (FU_PUSH + 8 * 2 * RLM_NWIN)
+#define FU_Q (FU_FLAG + 16)
+#define FU_SS (FU_Q + 8 * 2 * RLM_MAX_ACTIONS)
+#define FU_VBUF (FU_SS + 4 * SS_SLOTS)
+size_t rlm_fused_smem_bytes(int is_double) {
+  size_t per_warp = ((sizeof(EnvHdr) + 15) & ~(size_t)15) + (((size_t)FU_VBUF + (size_t)(is_double ? 2 : 1) * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
+  return FUSED_WARPS * per_warp;
+}
+
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 2) rlm_fused_kernel(DevPtrs ptr, DynParams D) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env = blockIdx.x * FUSED_WARPS + warp;
+  if (env >= P.n_envs) return;
+  const int hdr_bytes = (int)((sizeof(EnvHdr) + 15) & ~(size_t)15);
+  const size_t per_warp = hdr_bytes + (((size_t)FU_VBUF + (size_t)(P.is_double ? 2 : 1) * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
+  unsigned char* wbase = smem + (size_t)warp * per_warp;
+  EnvHdr& e = *(EnvHdr*)wbase;
+  unsigned char* sb = wbase + hdr_bytes;
+  rlm_tick_msg& msg = *(rlm_tick_msg*)(sb + FU_MSG);
+  double* pushv = (double*)(sb + FU_PUSH);
+  double* oldv = pushv + RLM_NWIN;
+  int* flag = (int*)(sb + FU_FLAG);
+  AgentScratch sc;
+  sc.q_pre = (double*)(sb + FU_Q); sc.sset = (int*)(sb + FU_SS); sc.idx = nullptr; sc.vbuf = (double*)(sb + FU_VBUF);
+  EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
+  double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
+  if (g->phase == PH_DONE) return;
+  {
+    const int4* src = (const int4*)g;
+    int4* dst = (int4*)&e;
+    for (int i = lane; i < hdr_bytes / 16; i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  unsigned long long ticked = 0, steps_done = 0, sum_z = 0;
+  unsigned long long* mt_pol = ptr.mt_pol + (size_t)env * 312;
+#pragma unroll 1
+  for (int t = 0; t < D.n_ticks; ++t) {
+    const int phase = e.phase;
+    if (phase == PH_DONE) break;
+    if (P.source == RLM_SOURCE_GENERATOR) {
+      if (lane == 0) flow_next_dev(&e.flow, &msg);
+    } else {
+      const int pos = D.stream_off + t;
+      if (pos >= D.stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; break; }
+      ((unsigned*)&msg)[lane] = __ldg((const unsigned*)(ptr.stream + ((size_t)pos * P.n_envs + env)) + lane);
+    }
+    if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);
+    __syncwarp();
+    if (phase == PH_PREOPEN) {  // intraday.cpp:111-116
+      if (lane == 0) {
+        msg.n_tx = 0;
+        update_book_profiles(e, msg);
+        if (market_is_open(e)) e.phase = PH_WARMUP;
+      }
+      __syncwarp();
+      continue;
+    }
+    ticked++;
+    if (lane == 0) {
+      if (phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
+      next_state_scalar(e, msg, pushv);       // Intraday::NextState
+    }
+    __syncwarp();
+    if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
+    __syncwarp();
+    if (lane == 0) {
+      int r = -1;
+      e.tp_val = e.w_mean[W_TP];
+      if (phase == PH_WARMUP) {  // intraday.cpp:118-135
+        bool full = true;
+        for (int w = 0; w < 8; ++w) full = full && (e.w_count[w] == P.win_size[w]);
+        if (full) { place_orders(e, 1, 1); e.phase = PH_RUN; e.ag.kind = 1; r = 1; }
+      } else {  // tail of one iteration of performAction's do-while (base.cpp:292-305)
+        double mpm = m_midprice(e) - m_last_midprice(e);
+        e.pnl_step += (double)e.position * mpm;
+        e.momentum_pnl_step += (double)e.position * mpm;
+        e.agg_r += get_reward(e);
+        e.agg_pnl += e.pnl_step;
+        e.agg_mpm += mpm;
+        if (!(!is_terminal(e) && fabs(e.agg_mpm) < 1e-5)) {
+          e.pnl_step = e.agg_pnl;  // base.cpp:317-331
+          pushv[W_PNLUP] = fmax(0.0, e.pnl_step);
+          pushv[W_PNLDN] = fabs(fmin(0.0, e.pnl_step));
+          e.ep_reward += e.agg_r;
+          e.ep_bandh += e.agg_mpm;
+          r = 0;
+        }
+      }
+      *flag = r;
+    }
+    __syncwarp();
+    const int ready = *flag;
+    if (ready < 0) continue;
+    if (ready == 0) {
+      if (lane == W_PNLUP || lane == W_PNLDN) window_push(e, ring, lane, pushv[lane], oldv[lane]);
+      __syncwarp();
+      if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
+      if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
+      __syncwarp();
+    }
+    agent_process_env(ptr, D, env, e.ag, sc, lane, steps_done, sum_z, 0, &e);  // serial.cpp:64-65
+    if (lane == 0) { begin_step(e, mt_pol, D); e.ag.need_begin = 0; }          // serial.cpp:55-61
+    __syncwarp();
+  }
+  __syncwarp();
+  {
+    int4* dst = (int4*)g;
+    const int4* src = (const int4*)&e;
+    for (int i = lane; i < hdr_bytes / 16; i += 32) dst[i] = src[i];
+  }
+  if (lane == 0) {
+    if (ticked) atomicAdd(&ptr.counters[0], ticked);
+    if (steps_done | sum_z) { atomicAdd(&ptr.counters[1], steps_done); atomicAdd(&ptr.counters[2], sum_z); }
+    const unsigned errs = (unsigned)(e.err | e.ag.err);
+    if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
+  }
+}
+
+cudaError_t rlm_launch_fused(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, cudaStream_t st) {
+  const size_t smem = rlm_fused_smem_bytes(is_double);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(rlm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  rlm_fused_kernel<<<(n_envs + FUSED_WARPS - 1) / FUSED_WARPS, FUSED_WARPS * 32, smem, st>>>(ptr, D);
   return cudaGetLastError();
 }
 
@@ -638,7 +791,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 4) rlm_run_kernel(DevPtrs ptr, Dy
       env = __shfl_sync(FULL, env, 0);
       if (env < 0) break;
       __threadfence();  // acquire: the env record published before the push
-      agent_process_env(ptr, D, env, ag, scratch, lane, steps_done, sum_z, 0);
+      agent_process_env(ptr, D, env, ag, std_scratch(scratch), lane, steps_done, sum_z, 0, nullptr);
       __threadfence();  // release: agent block, theta, traces
       if (lane == 0) *(volatile int*)(ptr.ag_done + env) = 1;
     }
