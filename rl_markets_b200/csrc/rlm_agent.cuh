@@ -150,11 +150,17 @@ __device__ __forceinline__ double seg_sum(double acc, double w, const double* r)
 // 32..64 dependent multiply-adds of the previous one.
 struct QGather { double a[RLM_MAX_ACTIONS]; double b[RLM_MAX_ACTIONS]; };
 
+// theta starts at +0.0 and only trace_pass writes it, so an entry whose bit in the per-policy
+// occupancy bitmap is clear is known to be exactly +0.0 and is not fetched.  The bitmap (M/8 bytes per
+// policy, 32 MB for 4096 x 2^16) stays L2-resident, whereas theta (2 GB) does not: the test turns most
+// of a step's 864 random DRAM sector reads -- the measured limiter of the agent kernel -- into L2 hits.
+__device__ __forceinline__ bool occ_test(const unsigned* occ, int f) { return (__ldcg(occ + (f >> 5)) >> (f & 31)) & 1u; }
+
 // idx: this warp's [27][32] tile-index cache in shared memory (row g*9+a, column lane).  The first
 // evaluation of a step fills it, the second one (same state, updated theta) just reads it back.
 __device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
                                         bool null_state, int g, int lane, unsigned long long* bases, bool reuse, int* idx,
-                                        QGather& out) {
+                                        const unsigned* occ, QGather& out) {
   const int A = P.n_actions;
   int f[RLM_MAX_ACTIONS];
   if (reuse && idx) {
@@ -174,26 +180,29 @@ __device__ __forceinline__ void q_issue(const unsigned* rnd, const double* th_a,
       if (a < A && idx) idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane] = f[a];
     }
   }
+  bool nz[RLM_MAX_ACTIONS];
 #pragma unroll
-  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.a[a] = (a < A) ? __ldcg(th_a + f[a]) : 0.0;  // L2-coherent: theta is rewritten by trace_pass, possibly from another SM
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) nz[a] = (a < A) && (occ == nullptr || occ_test(occ, f[a]));  // occ == nullptr: dense table
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.a[a] = nz[a] ? __ldcg(th_a + f[a]) : 0.0;  // L2-coherent: theta is rewritten by trace_pass, possibly from another SM
   if (th_b) {
 #pragma unroll
-    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.b[a] = (a < A) ? __ldcg(th_b + f[a]) : 0.0;
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) out.b[a] = nz[a] ? __ldcg(th_b + f[a]) : 0.0;
   }
 }
 
 __device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, const double* th_b, const float* vars, int n,
                        bool null_state, double* vbuf, int lane, double& qa_out, double& qb_out,
-                       unsigned long long* bases, bool reuse, int* idx) {
+                       unsigned long long* bases, bool reuse, int* idx, const unsigned* occ) {
   const int A = P.n_actions;
   double qa = 0.0, qb = 0.0;
   double* va = vbuf;
   double* vb = vbuf + RLM_MAX_ACTIONS * VROW;
   QGather cur, nxt;
-  q_issue(rnd, th_a, th_b, vars, n, null_state, 0, lane, bases, reuse, idx, cur);
+  q_issue(rnd, th_a, th_b, vars, n, null_state, 0, lane, bases, reuse, idx, occ, cur);
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    if (g < 2) q_issue(rnd, th_a, th_b, vars, n, null_state, g + 1, lane, bases, reuse, idx, nxt);
+    if (g < 2) q_issue(rnd, th_a, th_b, vars, n, null_state, g + 1, lane, bases, reuse, idx, occ, nxt);
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
       if (a < A) {
@@ -297,7 +306,7 @@ __device__ __forceinline__ int last_writer(const int* ss, int f, bool null_from,
   return la;
 }
 
-__device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, double* theta, int action, float rate,
+__device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, double* theta, unsigned* occ, int action, float rate,
                                        double scaled_update, int lane) {
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];
@@ -354,11 +363,16 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
       add = add && (pos < P.trace_cap);
       total = P.trace_cap;
     }
+    bool fresh = false;
     if (add) {
       __stcg(tf + pos, f);
       __stcg(te + pos, 1.0f);
+      const unsigned bit = 1u << (f & 31);
+      fresh = !(atomicOr(occ + (f >> 5), bit) & bit);  // every list entry was appended here once: its bit is set
       atomicAdd(theta + f, scaled_update * (double)1.0f);
     }
+    const int n_fresh = __popc(__ballot_sync(FULL, fresh));
+    if (lane == 0) e.n_occ += n_fresh;
     w = total;
   }
   __syncwarp();

@@ -17,6 +17,7 @@
 #include "rlm_rndseq.h"
 #include "rlm_kernels.h"
 #include <limits.h>
+#include <stddef.h>
 #include <stdlib.h>
 
 static thread_local std::string g_err;
@@ -39,6 +40,7 @@ struct rlm_handle_s {
   int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent queue (rlm_run_kernel), 2 fused (warp per env)
   int n_agent_ctas = 0;  // persistent engine: CTAs in the agent role
   int env_variant = 0;   // env tick kernel: 0 = warp per env, 1 = thread per env
+  int agent_variant = 3; // agent kernel: 3 = three warps per env, 1 = one warp per env
   unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
   DynParams shared_dyn;
   bool in_run = false;
@@ -130,6 +132,7 @@ static int derive(rlm_handle_s* h) {
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a)  // hash_UNH term of the action integer for feature group 0 (3 floats + tiling + int)
     p.ra_m[a] = (int)((unsigned long long)rlm_rndseq_table[(a + 449 * 4) & 2047] % (unsigned long long)c.memory_size);
   p.scratch_bytes = (int)rlm_scratch_bytes(p.is_double);
+  p.occ_words = (int)((c.memory_size + 31) / 32);
   p.gl = (float)(c.gamma * c.lambda);  // Traces::decay(float rate) narrows gamma*lambda (A11)
   for (int i = 0; i < 3; ++i) p.gw[i] = c.group_weights[i];
   p.gamma = c.gamma;
@@ -197,6 +200,11 @@ static int derive(rlm_handle_s* h) {
   return RLM_OK;
 }
 
+static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tslot, int stage) {
+  if (h->agent_variant == 3) return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, tslot, h->n_sms, stage, h->stream);
+  return rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, tslot, h->n_sms, stage, h->stream);
+}
+
 static int upload_params(rlm_handle_s* h) {
   if (g_params_owner != h) {
     CK(rlm_upload_params(&h->hp));
@@ -231,6 +239,12 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   if (p.is_double) {
     CK(cudaMalloc(&h->ptr.theta_b, th_bytes));
     CK(cudaMemsetAsync(h->ptr.theta_b, 0, th_bytes, h->stream));
+  }
+  {
+    // occupancy bitmap: clear = "theta entry is still exactly +0.0"; random_init makes every entry nonzero
+    size_t obytes = (size_t)h->n_policies * (size_t)p.occ_words * 4;
+    CK(cudaMalloc(&h->ptr.occ, obytes));
+    CK(cudaMemsetAsync(h->ptr.occ, cfg->random_init ? 0xFF : 0x00, obytes, h->stream));
   }
   if (cfg->shared_policy) {
     size_t dbytes = (size_t)(p.is_double ? 2 : 1) * (size_t)p.memory_size * 8;
@@ -291,6 +305,7 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
     h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
     if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
+    if (const char* s = getenv("RLM_AGENT_VARIANT")) h->agent_variant = (atoi(s) == 1) ? 1 : 3;
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
@@ -306,7 +321,7 @@ int rlm_destroy(rlm_handle h) {
   cudaFree(h->ptr.env); cudaFree(h->ptr.theta); cudaFree(h->ptr.theta_b); cudaFree(h->ptr.dtheta);
   cudaFree(h->ptr.trace_f); cudaFree(h->ptr.trace_e); cudaFree(h->ptr.mt_pol); cudaFree(h->ptr.mt_agt);
   cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters); cudaFree(h->d_stream);
-  cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count);
+  cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count); cudaFree(h->ptr.occ);
   cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
   for (auto e : h->ev) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -411,7 +426,7 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
       if (h->profile) CK(cudaEventRecord(h->ev[3 * t], h->stream));
       CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->env_variant, h->stream));
       if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 1], h->stream));
-      CK(rlm_launch_agent(h->ptr, dt, h->cfg.n_envs, h->hp.scratch_bytes, t, h->n_sms, 0, h->stream));
+      CK(launch_agent_any(h, dt, t, 0));
       if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 2], h->stream));
       h->launches += 2;
     }
@@ -556,6 +571,11 @@ int rlm_write_theta(rlm_handle h, int32_t policy, int32_t table, const double* i
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemcpy(dst + (size_t)policy * h->cfg.memory_size, in, (size_t)n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(h->ptr.occ + (size_t)policy * h->hp.occ_words, 0xFF, (size_t)h->hp.occ_words * 4));  // caller-provided weights: assume dense
+  if (!h->cfg.shared_policy) {
+    const int dense = (int)h->cfg.memory_size;
+    CK(cudaMemcpy(h->ptr.env + (size_t)policy * h->hp.env_stride + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), &dense, 4, cudaMemcpyHostToDevice));
+  }
   return RLM_OK;
 }
 
@@ -598,7 +618,7 @@ int rlm_shared_tick_accumulate(rlm_handle h) {
   }
   CK(cudaMemsetAsync(h->ptr.ready_count, 0, 4, h->stream));
   CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 0, h->env_variant, h->stream));
-  CK(rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 1, h->stream));
+  CK(launch_agent_any(h, d, 0, 1));
   h->launches += 2;
   h->shared_dyn = d;
   return RLM_OK;
@@ -616,7 +636,7 @@ int rlm_apply_dtheta(rlm_handle h) {
   CK(rlm_launch_apply_dtheta(h->ptr.theta, h->ptr.dtheta, h->cfg.memory_size, h->n_sms, h->stream));
   if (h->hp.is_double) CK(rlm_launch_apply_dtheta(h->ptr.theta_b, h->ptr.dtheta + h->cfg.memory_size, h->cfg.memory_size, h->n_sms, h->stream));
   (void)n;
-  CK(rlm_launch_agent(h->ptr, h->shared_dyn, h->cfg.n_envs, h->hp.scratch_bytes, 0, h->n_sms, 2, h->stream));
+  CK(launch_agent_any(h, h->shared_dyn, 0, 2));
   CK(rlm_launch_env(h->ptr, h->shared_dyn, h->cfg.n_envs, 0, 1, h->env_variant, h->stream));
   h->launches += 3;
   return RLM_OK;

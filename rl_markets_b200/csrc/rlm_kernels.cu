@@ -107,6 +107,7 @@ __global__ void rlm_random_init_kernel(DevPtrs ptr, int n_policies) {
   unsigned long long* x = ptr.mt_agt + (size_t)b * 312;
   double* th = ptr.theta + (size_t)b * P.memory_size;
   for (long long i = 0; i < P.memory_size; ++i) th[i] = 2.0 * mt_uniform_real(x, e->ag.mt_agt_idx) - 1.0;
+  e->ag.n_occ = (int)P.memory_size;  // dense from the start
   if (ptr.theta_b) {
     double* tb = ptr.theta_b + (size_t)b * P.memory_size;
     for (long long i = 0; i < P.memory_size; ++i) tb[i] = 2.0 * mt_uniform_real(x, e->ag.mt_agt_idx) - 1.0;
@@ -478,13 +479,16 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   const size_t pol = P.shared_policy ? 0 : (size_t)env;
   double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
   double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
+  unsigned* occ_w = ptr.occ + pol * (size_t)P.occ_words;
+  // once a quarter of an env's table is nonzero the bitmap test costs more than it saves: gather directly
+  const unsigned* occ = (!P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size) ? nullptr : occ_w;
   unsigned long long bases[3];
   if (stage == 2) {
     if (ag.kind == 0) {
       if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
       __syncwarp();
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc);
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc, occ);
       if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       ag.from_base0[lane] = mod_m(bases[0]);
       if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
@@ -493,7 +497,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   } else if (ag.kind == 1) {
     // end of warm-up: Q(null state, .) for the very first action selection
     double qa, qb;
-    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false, idxc);
+    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false, idxc, occ);
     if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
     if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; ag.kind = 2; }
   } else {
@@ -503,13 +507,13 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       // shared theta moved since the action was selected: UpdateTraces / UpdateWeights read Q(from, .)
       // under the theta of NOW (agent.cpp:274,285 call getQ at update time), i.e. theta_t
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, ag.null_from != 0, vbuf, lane, qa, qb, bases, false, idxc);
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, ag.null_from != 0, vbuf, lane, qa, qb, bases, false, idxc, occ);
       if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       __syncwarp();
     }
     {  // Q(to, .) under the current theta
       double qa, qb;
-      eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc);
+      eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc, occ);
       if (lane < A) { q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
     }
     __syncwarp();
@@ -522,7 +526,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       double* th = (dec[2] != 0.0) ? theta_b : theta_a;
       if (stage == 1) th = (dec[2] != 0.0) ? ptr.dtheta + P.memory_size : ptr.dtheta;  // accumulate, apply after the all-reduce
       __syncwarp();
-      int nz = trace_pass(ag, sset, tf, te, th, ag.cur_action, rate, scaled, lane);
+      int nz = trace_pass(ag, sset, tf, te, th, occ_w, ag.cur_action, rate, scaled, lane);
       if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
       sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
     }
@@ -553,7 +557,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       __syncwarp();
       {
         double qa, qb;
-        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true, idxc);
+        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true, idxc, occ);
         if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       }
       steps_done++;
@@ -566,6 +570,206 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
     for (int i = lane; i < (int)(AG_BYTES / 16); i += 32) __stcg(dst + i, src[i]);
   }
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Learner step with THREE warps per ready env (one CTA of 96 threads per env; default): warp g hashes
+// feature group g and issues its 9 (18) theta gathers at once, so the three groups' DRAM round trips
+// overlap and the hashing chain is a third as long; warp 0 then does the exact-order sums, the TD
+// decision and the trace pass; the second evaluation re-gathers with the indices still in registers.
+#define A3_WARPS 3
+#define A3_Q 0                                             // q_pre_a, q_pre_b: 18 doubles
+#define A3_SS (A3_Q + 8 * 2 * RLM_MAX_ACTIONS)             // small set
+#define A3_DEC (A3_SS + 4 * SS_SLOTS)                      // 4 doubles
+#define A3_V (A3_DEC + 32)                                 // V[table][g][a][VROW]
+size_t rlm_agent3_smem_bytes(int is_double) {
+  return AG_BYTES + (((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 3 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
+}
+
+// indices of lane j's tiles of group g for every action (registers), and the partial hash sum
+__device__ __forceinline__ unsigned long long a3_hash(const unsigned* rnd, const float* vars, int n, bool null_state, int g, int lane,
+                                                      int* f) {
+  const int A = P.n_actions;
+  const float* gv = (g == 1) ? vars + 3 : vars;
+  const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
+  unsigned long long base = 0ull;
+  if (!null_state) base = tile_base_sum(rnd, gv, nf, lane);
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
+  return base;
+}
+__device__ __forceinline__ void a3_gather(const double* th_a, const double* th_b, const unsigned* occ, const int* f, int g, int lane, double* V) {
+  const int A = P.n_actions;
+  double va[RLM_MAX_ACTIONS], vb[RLM_MAX_ACTIONS];
+  bool nz[RLM_MAX_ACTIONS];
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) nz[a] = (a < A) && (occ == nullptr || occ_test(occ, f[a]));  // occ == nullptr: dense table
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) va[a] = nz[a] ? __ldcg(th_a + f[a]) : 0.0;
+  if (th_b) {
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) vb[a] = nz[a] ? __ldcg(th_b + f[a]) : 0.0;
+  }
+  double* Va = V + (size_t)g * RLM_MAX_ACTIONS * VROW;
+  double* Vb = V + (size_t)(3 + g) * RLM_MAX_ACTIONS * VROW;
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+    if (a < A) {
+      Va[a * VROW + lane] = va[a];
+      if (th_b) Vb[a * VROW + lane] = vb[a];
+    }
+  }
+}
+// exact-order sums of agent.cpp:117-135 over the three gathered groups; lanes < A of warp 0
+__device__ __forceinline__ void a3_sums(const double* V, bool has_b, int lane, double& qa, double& qb) {
+  qa = 0.0; qb = 0.0;
+#pragma unroll 1
+  for (int seg = 0; seg < 4; ++seg) {  // (g0,w0) (g1,w1) (g1,w2) (g2,w2): the third loop starts at T (Appendix A8)
+    const int g = (seg == 0) ? 0 : ((seg == 3) ? 2 : 1);
+    const double w = P.gw[(seg == 0) ? 0 : ((seg == 1) ? 1 : 2)];
+    qa = seg_sum(qa, w, V + ((size_t)g * RLM_MAX_ACTIONS + lane) * VROW);
+    if (has_b) qb = seg_sum(qb, w, V + ((size_t)(3 + g) * RLM_MAX_ACTIONS + lane) * VROW);
+  }
+}
+
+__global__ void __launch_bounds__(A3_WARPS * 32, 8) rlm_agent3_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  AgentD& ag = *(AgentD*)smem;
+  unsigned char* sb = smem + AG_BYTES;
+  double* q_pre_a = (double*)(sb + A3_Q);
+  double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
+  int* sset = (int*)(sb + A3_SS);
+  double* dec = (double*)(sb + A3_DEC);
+  double* V = (double*)(sb + A3_V);
+  const unsigned* rnd = rlm_rndseq_table;
+  const int A = P.n_actions;
+  const int n_ready = ptr.ready_count[tslot];
+  unsigned long long steps_done = 0, sum_z = 0;
+#pragma unroll 1
+  for (int idx = blockIdx.x; idx < n_ready; idx += gridDim.x) {
+    const int env = ptr.ready[idx];
+    EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
+    __syncthreads();  // previous env's shared state is dead
+    {
+      const int4* src = (const int4*)&g->ag;
+      int4* dst = (int4*)&ag;
+      for (int i = tid; i < (int)(AG_BYTES / 16); i += A3_WARPS * 32) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    const size_t pol = P.shared_policy ? 0 : (size_t)env;
+    double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
+    double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
+    unsigned* occ_w = ptr.occ + pol * (size_t)P.occ_words;
+    const unsigned* occ = (!P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size) ? nullptr : occ_w;
+    const int kind = ag.kind;
+    int f[RLM_MAX_ACTIONS];
+    unsigned long long base = 0ull;
+    if (stage == 2) {
+      if (kind == 0) {  // shared policy, after theta += dtheta: Q(from = to-state, .) under theta_{t+1}
+        base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);
+        a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+        __syncthreads();
+        if (warp == 0) {
+          double qa, qb;
+          if (lane < A) { a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          ag.from_base0[lane] = mod_m(base);
+          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          steps_done++;
+        }
+      }
+    } else if (kind == 1) {  // end of warm-up: Q(null state, .)
+      a3_hash(rnd, ag.from_vars, P.n_state_vars, true, warp, lane, f);
+      a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+      __syncthreads();
+      if (warp == 0) {
+        double qa, qb;
+        if (lane < A) { a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+        if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; ag.kind = 2; }
+      }
+    } else if (kind == 0) {
+      if (stage == 1) {  // shared policy: Q(from, .) under theta_t (agent.cpp:274,285 read theta at update time)
+        a3_hash(rnd, ag.from_vars, P.n_state_vars, ag.null_from != 0, warp, lane, f);
+        a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+        __syncthreads();
+        if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+        __syncthreads();
+      }
+      base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);  // Q(to, .) under the current theta
+      a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+      __syncthreads();
+      if (warp == 0) {
+        int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
+        float* te = ptr.trace_e + (size_t)env * P.trace_cap;
+        if (lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
+        __syncwarp();
+        if (lane == 0)
+          td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr, D, dec);
+        __syncwarp();
+        const float rate = (float)dec[0];
+        const double scaled = dec[1];
+        double* th = (dec[2] != 0.0) ? theta_b : theta_a;
+        if (stage == 1) th = (dec[2] != 0.0) ? ptr.dtheta + P.memory_size : ptr.dtheta;
+        int nz = trace_pass(ag, sset, tf, te, th, occ_w, ag.cur_action, rate, scaled, lane);
+        if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
+        sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
+        __syncwarp();
+        __threadfence();
+        if (env < P.record_envs) {
+          unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
+          if (lane == 0) {
+            int c = ptr.record_count[env];
+            if (c < P.record_cap) {
+              EnvHdr tmp;
+              const int4* src = (const int4*)g;
+              int4* dst = (int4*)&tmp;
+              for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
+              fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h);
+            }
+            ptr.record_count[env] = c + 1;
+          }
+        }
+        if (stage == 0) {
+          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          ag.from_base0[lane] = mod_m(base);
+          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          steps_done++;
+        }
+      }
+      if (stage == 0) {  // Q(from = to-state, .) under the UPDATED theta (serial.cpp:55,60); indices are still in registers
+        __syncthreads();
+        a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+        __syncthreads();
+        if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+      }
+    }
+    __syncthreads();
+    {
+      int4* dst = (int4*)&g->ag;
+      const int4* src = (const int4*)&ag;
+      for (int i = tid; i < (int)(AG_BYTES / 16); i += A3_WARPS * 32) __stcg(dst + i, src[i]);
+    }
+  }
+  if (tid == 0 && (steps_done | sum_z)) {
+    atomicAdd(&ptr.counters[1], steps_done);
+    atomicAdd(&ptr.counters[2], sum_z);
+  }
+}
+
+cudaError_t rlm_launch_agent3(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int tslot, int n_sms, int stage, cudaStream_t st) {
+  const size_t smem = rlm_agent3_smem_bytes(is_double);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(rlm_agent3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  int grid = n_envs;            // worst case: every env is ready
+  const int cap = n_sms * 16;   // then the grid-stride loop takes over
+  if (grid > cap) grid = cap;
+  rlm_agent3_kernel<<<grid, A3_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
+  return cudaGetLastError();
 }
 
 // Tick-synchronous engine: one launch per tick after rlm_env_kernel.

@@ -62,7 +62,9 @@ struct alignas(16) AgentD {
   int n_traces, cur_action;
   int need_begin;  // the next env tick starts with Learner::_step's action selection (serial.cpp:55-61)
   int kind;        // why the env is in the ready list: 0 learner step, 1 end of warm-up
-  int ep_step, err, pad;
+  int ep_step, err;
+  int n_occ;   // independent policies: bits set in this env's occupancy bitmap; > M/4 => treat theta as dense
+  int pad[3];
 };
 
 struct EnvHdr {
@@ -110,6 +112,7 @@ struct DevParams {
   int env_stride;       // bytes per env record in HBM (multiple of 16)
   int trace_cap, record_envs, record_cap;
   int scratch_bytes;    // per-warp shared-memory scratch (depends on is_double)
+  int occ_words;        // 32-bit words of the occupancy bitmap per policy
   long long env_index0;
   VenueD venue;
   rlm_flow_params flow;
@@ -138,6 +141,7 @@ struct DevPtrs {
   rlm_step_record* records;    // [record_envs][record_cap]
   int* record_count;           // [record_envs]
   unsigned long long* counters;  // [8]: ticks, steps, sum_traces, terminal, err
+  unsigned* occ;                 // [n_policies][occ_words] occupancy bitmap: bit f set <=> theta[f] was ever updated
   int* ready;                    // [n_envs] env indices that need the agent kernel this tick
   int* ready_count;              // [ticks of the current run call]
   // persistent engine
