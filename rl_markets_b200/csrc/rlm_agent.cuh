@@ -116,13 +116,20 @@ __device__ __forceinline__ int tile_coord(int q, int i, int j) {
 // Partial hash sum (everything except the action-dependent integer) for lane j's tiling of one
 // feature group: floats vars[0..nf) then the tiling index (tiles.cpp:65-68, hash_UNH :152-161).
 __device__ __noinline__ unsigned long long tile_base_sum(const unsigned* rnd, const float* vars, int nf, int j) {
-  unsigned long long sum = 0;
-  for (int i = 0; i < nf; ++i) {
-    int q = (int)floorf(vars[i] * (float)RLM_N_TILINGS);
-    int c = tile_coord(q, i, j);
-    sum += __ldg(rnd + ((c + 449 * i) & 2047));
+  // fully unrolled and predicated so that the table lookups (L1/L2 round trips) are all in flight together
+  unsigned v[RLM_N_STATE_MAX];
+#pragma unroll
+  for (int i = 0; i < RLM_N_STATE_MAX; ++i) {
+    v[i] = 0u;
+    if (i < nf) {
+      int q = (int)floorf(vars[i] * (float)RLM_N_TILINGS);
+      int c = tile_coord(q, i, j);
+      v[i] = __ldg(rnd + ((c + 449 * i) & 2047));
+    }
   }
-  sum += __ldg(rnd + ((j + 449 * nf) & 2047));
+  unsigned long long sum = __ldg(rnd + ((j + 449 * nf) & 2047));
+#pragma unroll
+  for (int i = 0; i < RLM_N_STATE_MAX; ++i) sum += v[i];
   return sum;
 }
 __device__ __forceinline__ int tile_index(const unsigned* rnd, unsigned long long base, int nf, int h1) {

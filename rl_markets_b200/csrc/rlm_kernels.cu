@@ -632,7 +632,7 @@ __device__ __forceinline__ void a3_sums(const double* V, bool has_b, int lane, d
   }
 }
 
-__global__ void __launch_bounds__(A3_WARPS * 32, 8) rlm_agent3_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
+__global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   AgentD& ag = *(AgentD*)smem;
