@@ -163,13 +163,28 @@ RLM_HD void rlm_flow_shift(int32_t v[RLM_DEPTH], int d, const uint32_t fresh[3])
 /* Produce message number s->tick and advance the state.
  * skellam: 4096-entry int8 LUT, pois30: 4096-entry uint8 LUT, pois1p5: 256-entry uint8 LUT
  * (rlm_flow_tables.h; on the device these live in shared memory). */
+/* The three Philox draws of tick s->tick (call = 0, 1, 2); independent of each other, so a warp can
+ * evaluate them on three lanes. */
+RLM_HD void rlm_flow_draw(const rlm_flow_state* s, uint32_t call, uint32_t out[4]) {
+  rlm_philox4x32((uint32_t)s->tick, call, 0u, 0x524C4D31u, s->key0, s->key1, out);
+}
+
+RLM_HD void rlm_flow_apply(rlm_flow_state* s, const rlm_flow_params* p, const int8_t* skellam, const uint8_t* pois30,
+                           const uint8_t* pois1p5, const uint32_t r0[4], const uint32_t r1[4], const uint32_t r2[4],
+                           rlm_tick_msg* m);
+
 RLM_HD void rlm_flow_next(rlm_flow_state* s, const rlm_flow_params* p, const int8_t* skellam,
                           const uint8_t* pois30, const uint8_t* pois1p5, rlm_tick_msg* m) {
   uint32_t r0[4], r1[4], r2[4];
-  const uint32_t t = (uint32_t)s->tick;
-  rlm_philox4x32(t, 0u, 0u, 0x524C4D31u, s->key0, s->key1, r0);
-  rlm_philox4x32(t, 1u, 0u, 0x524C4D31u, s->key0, s->key1, r1);
-  rlm_philox4x32(t, 2u, 0u, 0x524C4D31u, s->key0, s->key1, r2);
+  rlm_flow_draw(s, 0u, r0);
+  rlm_flow_draw(s, 1u, r1);
+  rlm_flow_draw(s, 2u, r2);
+  rlm_flow_apply(s, p, skellam, pois30, pois1p5, r0, r1, r2, m);
+}
+
+RLM_HD void rlm_flow_apply(rlm_flow_state* s, const rlm_flow_params* p, const int8_t* skellam, const uint8_t* pois30,
+                           const uint8_t* pois1p5, const uint32_t r0[4], const uint32_t r1[4], const uint32_t r2[4],
+                           rlm_tick_msg* m) {
 
   /* ---- prints against the PRE-update book (prices of the previous row) ---- */
   const int32_t pa = s->bid_tick + s->spread, pb = s->bid_tick;

@@ -418,21 +418,16 @@ __device__ __noinline__ void update_book_profiles(EnvHdr& e, const rlm_tick_msg&
   e.time_ms = m.time_ms;
   side_apply_changes(e.side[0], m.ask_px, m.ask_vol, m, &e.err);
   side_apply_changes(e.side[1], m.bid_px, m.bid_vol, m, &e.err);
-  // BookUtils::IsValidState (book.cpp:612-625); the reference would swallow further rows
   if (e.side[0].has_last && e.side[1].has_last && !(pkey(e.side[0].last_px[0]) == 0.0) && !(pkey(e.side[1].last_px[0]) == 0.0)) {
-    double mp = m_midprice(e);
+    double mp = m_midprice(e);  // BookUtils::IsValidState (book.cpp:612-625); the reference would swallow further rows
     bool ok = (m_spread(e) >= 0.0) && (mp > 0.0) && (fabs(mp - m_last_midprice(e)) < mp);
     if (!ok) e.err |= ERR_INVALID_STATE;
   }
 }
 
-// Intraday::NextState (intraday.cpp:224-272) up to the window pushes; the eight values to
-// push are returned in pushv[W_MID..W_BIDTX] and applied lane-parallel by the caller.
-__device__ __noinline__ void next_state_scalar(EnvHdr& e, const rlm_tick_msg& m, double* pushv) {
-  double mp = m_midprice(e);
-  Fill au = side_apply_transactions<true>(e.side[0], m, mp, true);
-  Fill bu = side_apply_transactions<false>(e.side[1], m, mp, true);
-  update_book_profiles(e, m);
+// second half of NextState (intraday.cpp:242-269): adverse selection, P&L / position book-keeping, the
+// eight values to push into the rolling windows
+__device__ __noinline__ void next_state_tail(EnvHdr& e, const Fill& au, const Fill& bu, double* pushv) {
   Fill as = adverse_selection(e);
   e.pnl_step += au.proxy + bu.proxy + as.proxy;
   long long asabs = as.volume < 0 ? -as.volume : as.volume;
@@ -455,6 +450,45 @@ __device__ __noinline__ void next_state_scalar(EnvHdr& e, const rlm_tick_msg& m,
   e.ewma_up = (P.ewma_alpha * fmax(0.0, mpm)) + ((1 - P.ewma_alpha) * e.ewma_up);
   e.ewma_dn = (P.ewma_alpha * fabs(fmin(0.0, mpm))) + ((1 - P.ewma_alpha) * e.ewma_dn);
   e.n_ticks++;
+}
+
+// BookUtils::IsValidState (book.cpp:612-625); the reference would swallow further rows
+__device__ __forceinline__ void check_valid_state(EnvHdr& e) {
+  if (e.side[0].has_last && e.side[1].has_last && !(pkey(e.side[0].last_px[0]) == 0.0) && !(pkey(e.side[1].last_px[0]) == 0.0)) {
+    double mp = m_midprice(e);
+    bool ok = (m_spread(e) >= 0.0) && (mp > 0.0) && (fabs(mp - m_last_midprice(e)) < mp);
+    if (!ok) e.err |= ERR_INVALID_STATE;
+  }
+}
+
+// Intraday::NextState (intraday.cpp:224-272) up to the window pushes, one thread.
+__device__ __noinline__ void next_state_scalar(EnvHdr& e, const rlm_tick_msg& m, double* pushv) {
+  double mp = m_midprice(e);
+  Fill au = side_apply_transactions<true>(e.side[0], m, mp, true);
+  Fill bu = side_apply_transactions<false>(e.side[1], m, mp, true);
+  update_book_profiles(e, m);
+  next_state_tail(e, au, bu, pushv);
+}
+
+// The same with the two book sides on two lanes (they are independent until adverse selection):
+// lane 0 = ask, lane 1 = bid.  `fills` = 2 Fill structs + 2 ints of this warp's shared memory.
+__device__ __noinline__ void next_state_warp(EnvHdr& e, const rlm_tick_msg& m, double* pushv, Fill* fills, int lane) {
+  int* serr = (int*)(fills + 2);
+  if (lane < 2) {
+    const double mp = m_midprice(e);  // pre-update midprice (intraday.cpp:235)
+    serr[lane] = 0;
+    fills[lane] = (lane == 0) ? side_apply_transactions<true>(e.side[0], m, mp, true)
+                              : side_apply_transactions<false>(e.side[1], m, mp, true);
+  }
+  __syncwarp();
+  if (lane < 2) side_apply_changes(e.side[lane], lane == 0 ? m.ask_px : m.bid_px, lane == 0 ? m.ask_vol : m.bid_vol, m, &serr[lane]);
+  __syncwarp();
+  if (lane == 0) {
+    e.last_date = e.date; e.date = m.date; e.time_ms = m.time_ms;  // intraday.cpp:286-288
+    e.err |= serr[0] | serr[1];
+    check_valid_state(e);
+    next_state_tail(e, fills[0], fills[1], pushv);
+  }
 }
 
 // Intraday::getVariable (intraday.cpp:315-409)

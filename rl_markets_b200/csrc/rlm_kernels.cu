@@ -173,6 +173,13 @@ __device__ __noinline__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, c
 __device__ __noinline__ void flow_next_dev(rlm_flow_state* s, rlm_tick_msg* m) {
   rlm_flow_next(s, &P.flow, rlm_flow_skellam20_lut, rlm_flow_pois30_lut, rlm_flow_pois1p5_lut, m);
 }
+// warp version: lanes 0..2 evaluate the three Philox calls, lane 0 applies them
+__device__ __noinline__ void flow_next_warp(rlm_flow_state* s, rlm_tick_msg* m, unsigned* r12 /* 12 words of shared memory */, int lane) {
+  if (lane < 3) rlm_flow_draw(s, (uint32_t)lane, r12 + 4 * lane);
+  __syncwarp();
+  if (lane == 0)
+    rlm_flow_apply(s, &P.flow, rlm_flow_skellam20_lut, rlm_flow_pois30_lut, rlm_flow_pois1p5_lut, r12, r12 + 4, r12 + 8, m);
+}
 
 // One market tick of one env (thread-per-env).  Returns -1, or the ready kind: 0 = a learner step
 // ended (state variables + reward are in e.ag), 1 = warm-up ended (Intraday::Initialise done).
@@ -298,12 +305,14 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   const int env = blockIdx.x * ENVW_WARPS + warp;
   if (env >= P.n_envs) return;
   const int hdr_bytes = (int)((sizeof(EnvHdr) + 15) & ~(size_t)15);
-  unsigned char* wbase = smem + (size_t)warp * (hdr_bytes + 128 + 8 * 2 * RLM_NWIN + 16);
+  unsigned char* wbase = smem + (size_t)warp * (hdr_bytes + 128 + 8 * 2 * RLM_NWIN + 128);
   EnvHdr& e = *(EnvHdr*)wbase;
   rlm_tick_msg& msg = *(rlm_tick_msg*)(wbase + hdr_bytes);
   double* pushv = (double*)(wbase + hdr_bytes + 128);
   double* oldv = pushv + RLM_NWIN;
   int* flag = (int*)(oldv + RLM_NWIN);
+  unsigned* r12 = (unsigned*)(flag + 4);
+  Fill* fills = (Fill*)(r12 + 12);  // 2 Fill + 2 ints
   EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
   double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
   {
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   if (!only_begin && e.phase != PH_DONE) {
     bool have = true;
     if (P.source == RLM_SOURCE_GENERATOR) {
-      if (lane == 0) flow_next_dev(&e.flow, &msg);
+      flow_next_warp(&e.flow, &msg, r12, lane);
     } else {
       const int pos = D.stream_off + tslot;
       if (pos >= D.stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; have = false; }
@@ -340,10 +349,9 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
       }
     } else if (have) {
       ticked = 1;
-      if (lane == 0) {
-        if (phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
-        next_state_scalar(e, msg, pushv);       // Intraday::NextState
-      }
+      if (lane == 0 && phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
+      __syncwarp();
+      next_state_warp(e, msg, pushv, fills, lane);  // Intraday::NextState, ask side on lane 0, bid side on lane 1
       __syncwarp();
       if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
       __syncwarp();
@@ -1110,7 +1118,7 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
     rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
     return cudaGetLastError();
   }
-  const size_t per_warp = ((sizeof(EnvHdr) + 15) & ~(size_t)15) + 128 + 8 * 2 * RLM_NWIN + 16;
+  const size_t per_warp = ((sizeof(EnvHdr) + 15) & ~(size_t)15) + 128 + 8 * 2 * RLM_NWIN + 128;
   const size_t smem = ENVW_WARPS * per_warp;
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
