@@ -390,7 +390,7 @@ def main():
     ap.add_argument("--e2e-distinct", type=int, default=64, help="distinct host-generated streams replayed across envs in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-ticks", type=int, default=400000)
-    ap.add_argument("--ref-ticks", type=int, default=200000)
+    ap.add_argument("--ref-ticks", type=int, default=100000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,9 +38,10 @@ __device__ __forceinline__ long long d2ll_x86(double d) {
 __device__ __noinline__ int to_ticks(double price, int* err) {
   const VenueD& V = P.venue;
   if (price < V.px[0]) { *err |= ERR_TICK_RANGE; return 0; }
-  int k = 0;  // band containing price: number of band starts px[1..n) that are <= price
+  int k = 0;  // band containing price = last band start <= price; binary search (px[i >= n] = +inf, px[0] <= price)
 #pragma unroll
-  for (int i = 1; i < RLM_MAX_BANDS; ++i) k += !(price < V.px[i]) ? 1 : 0;  // px[i >= n] = +inf
+  for (int step = RLM_MAX_BANDS / 2; step >= 1; step >>= 1)
+    if (!(price < V.px[k + step])) k += step;
   int ticks = V.cum_full[k];
   double tsp = V.ts[k];  // tick_size(price) = band containing price (market.cpp:130-138)
   int it = k;
@@ -60,9 +61,10 @@ __device__ __noinline__ double to_price(int ticks, int* err) {
   const VenueD& V = P.venue;
   if (ticks < V.tts_tick[0]) { *err |= ERR_TICK_RANGE; return 0.0; }
   if (!(ticks > V.tts_tick[0])) return 0.0;
-  int k = 0;
+  int k = 0;  // last tts_ key <= ticks (tts_tick[i >= n] = INT_MAX)
 #pragma unroll
-  for (int i = 1; i < RLM_MAX_BANDS; ++i) k += (ticks >= V.tts_tick[i]) ? 1 : 0;  // tts_tick[i >= n] = INT_MAX
+  for (int step = RLM_MAX_BANDS / 2; step >= 1; step >>= 1)
+    if (ticks >= V.tts_tick[k + step]) k += step;
   // bands 0..k-1 fully traversed; band k partially (or exactly to its end when ticks == next key)
   double price = V.cum_price[k];
   if (ticks > V.tts_tick[k]) price += ((double)ticks - (double)V.tts_tick[k]) * V.ts[k];

@@ -69,3 +69,19 @@ def test_csv_rendering_round_trips(oracle):
         assert [int(x) for x in c[17:22]] == list(m.bid_vol)
         tx = by_time.get(c[1], [])
         assert tx == [(m.tx_px[k], m.tx_vol[k]) for k in range(m.n_tx)]
+
+
+def test_csv_ingestion_reproduces_the_packed_stream(oracle):
+    """rl_markets_b200.ingest (reference CSV pair -> packed ticks) inverts oracle/_ref/flow_csv, and the
+    oracle fed with the ingested stream behaves like the reference fed with the CSV files."""
+    from rl_markets_b200 import ingest
+    cfg = _cfg(seed=17)
+    n = 1500
+    packed = lib.flow_generate(cfg.flow, 2, 0, n)
+    with tempfile.TemporaryDirectory() as d:
+        md, tas = os.path.join(d, "a_md_1.csv"), os.path.join(d, "a_tas_1.csv")
+        subprocess.check_call([oracle.FLOW_CSV, "--seed", "17", "--env", "2", "--ticks", str(n), "--md", md, "--tas", tas])
+        got = ingest.csv_pair_to_ticks(md, tas)
+    assert len(got) == n
+    # the first message's prints are dropped by the reference (SkipUntil); the generator emits none there
+    assert bytes(got) == bytes(packed)
