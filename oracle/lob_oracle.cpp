@@ -1232,6 +1232,15 @@ int64_t lobo_total_ticks(lobo_env* e) { return e->total_ticks; }
 int64_t lobo_sum_traces(lobo_env* e) { return e->sum_traces; }
 const double* lobo_theta(lobo_env* e, int table) { return table == 0 ? e->theta.data() : (e->theta_b.empty() ? nullptr : e->theta_b.data()); }
 void lobo_handle_terminal(lobo_env* e, int episode) { e->HandleTerminal(episode); }
+// next episode on a FRESH experiment::serial::Learner (never-populated States, serial.cpp:9-16): Intraday::Initialise
+// + rewound data.  (A Learner reused across episodes would carry a stale State over, src/main.cpp:48-58; that
+// carry-over is not part of rlm_reset's contract.)
+void lobo_reset(lobo_env* e) {
+  e->state1.init(e->c.memory_size, e->c.n_actions, e->c.n_tilings);
+  e->state2.init(e->c.memory_size, e->c.n_actions, e->c.n_tilings);
+  e->state = &e->state1; e->last_state = &e->state2;
+  e->reset_episode();
+}
 void lobo_go_greedy(lobo_env* e) { e->greedy = true; }
 
 int64_t lobo_run_batch(const rlm_config* cfg, int32_t n_envs, int64_t n_ticks, int32_t n_threads, int64_t* total_ticks,

@@ -66,6 +66,7 @@ def lib():
         L.lobo_theta.argtypes = [C.c_void_p, C.c_int]
         L.lobo_handle_terminal.argtypes = [C.c_void_p, C.c_int]
         L.lobo_go_greedy.argtypes = [C.c_void_p]
+        L.lobo_reset.argtypes = [C.c_void_p]
         L.lobo_run_batch.restype = C.c_int64
         L.lobo_run_batch.argtypes = [C.POINTER(abi.Config), C.c_int32, C.c_int64, C.c_int32,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_double)]
