@@ -174,6 +174,9 @@ int rlm_get_stats(rlm_handle h, int32_t env0, int32_t n, rlm_env_stats* out);
 int rlm_get_state(rlm_handle h, float* out /* [n_envs][n_state_vars] */);
 int rlm_get_reward(rlm_handle h, double* out /* [n_envs] last reward handed to the agent */);
 int rlm_get_actions(rlm_handle h, int32_t* out /* [n_envs] last action */);
+/* rho of the R-learning agents (RLearn / OnlineRLearn / DoubleRLearn private member, include/rl/agent.h:131,145,157;
+   the reference never prints it -- exposed here so that parity of the average-reward estimate can be checked) */
+int rlm_get_rho(rlm_handle h, double* out /* [n_envs] */);
 
 int rlm_handle_terminal(rlm_handle h, int32_t episode);
 int rlm_go_greedy(rlm_handle h);

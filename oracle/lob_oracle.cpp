@@ -9,6 +9,7 @@
 #include "lob_oracle.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -664,6 +665,8 @@ struct lobo_env {
   std::vector<double>& THB() { return sh_b ? *sh_b : theta_b; }
   bool is_double() const { return c.algorithm == RLM_ALGO_DOUBLE_Q_LEARN || c.algorithm == RLM_ALGO_DOUBLE_R_LEARN; }
   double alpha = 0, eps = 0, eps_init = 0, eps_floor = 0;
+  double tau = 0, tau_init = 0, tau_floor = 0;  // Boltzmann (policy.cpp:85-96; read as float, main.cpp:157-158)
+  double rho = 0.0;                             // R-learning average reward (agent.h:131,145,157)
   bool greedy = false;
   MT64 policy_gen, agent_gen;
   GlibcRand crand;
@@ -706,6 +709,8 @@ struct lobo_env {
     policy_gen.seed(seed);       // policy.cpp:13
     crand.seed(seed);            // main.cpp:87
     eps_init = (double)c.eps_init; eps = eps_init; eps_floor = (double)c.eps_floor;  // main.cpp:149-154
+    tau_init = (double)c.tau_init; tau = tau_init; tau_floor = (double)c.tau_floor;  // main.cpp:157-162
+    rho = 0.0;
     state1.init(c.memory_size, c.n_actions, c.n_tilings);
     state2.init(c.memory_size, c.n_actions, c.n_tilings);
     state = &state1; last_state = &state2;  // serial.cpp:14-15
@@ -986,7 +991,19 @@ struct lobo_env {
       case RLM_POLICY_EPSILON_GREEDY:                                          // :69-75
         if (uniform_real01(policy_gen) < eps) return uniform_int_n(policy_gen, c.n_actions);
         else return greedy_sample(qs);
-      default: throw std::runtime_error("oracle: policy not restated (boltzmann uses libm exp; parity unpinned)");
+      case RLM_POLICY_BOLTZMANN: {  // :98-115 (libm exp: bitwise only against the same libm)
+        std::vector<double> probabilities(c.n_actions, 0.0);
+        double z = 0.0;
+        for (int a = 0; a < c.n_actions; a++) { probabilities[a] = std::exp(qs[a] / tau); z += probabilities[a]; }
+        double acc = 0.0;
+        double r = uniform_real01(policy_gen);
+        for (int a = 0; a < c.n_actions; a++) {
+          acc += probabilities[a] / z;
+          if (r < acc) return a;
+        }
+        return c.n_actions - 1;
+      }
+      default: throw std::runtime_error("oracle: unknown policy");
     }
   }
   unsigned agent_action(State& s) {  // Agent::action :67-74 / DoubleAgent::action :202-209
@@ -1034,13 +1051,54 @@ struct lobo_env {
         }
         return delta;
       }
-      default: throw std::runtime_error("oracle: algorithm not restated");
+      case RLM_ALGO_R_LEARN: {  // :373-388
+        double Q = getQ(from, action), mQ = maxQ(to);
+        delta = reward - rho + mQ - Q;
+        double update = alpha * delta;
+        updateQ_tab(theta, update);
+        double nQ = Q + update;
+        if (nQ - maxQ(from) < 1e-7) rho += c.beta * (reward - rho + mQ - nQ);
+        return delta;
+      }
+      case RLM_ALGO_ONLINE_R_LEARN: {  // :398-413
+        double Q = getQ(from, action), gQ = getQ(to, (int)agent_action(to));
+        delta = reward - rho + gQ - Q;
+        double update = alpha * delta;
+        updateQ_tab(theta, update);
+        double nQ = Q + update;
+        if (nQ - maxQ(from) < 1e-7) rho += c.beta * (reward - rho + gQ - nQ);
+        return delta;
+      }
+      case RLM_ALGO_DOUBLE_R_LEARN: {  // :432-467
+        double Q, mQ;
+        if (uniform_real01(agent_gen) > 0.5) {
+          Q = getQ(from, action);
+          mQ = getQb(to, argmaxQ(to));
+          delta = reward - rho + mQ - Q;
+          updateQ_tab(theta, alpha * delta);
+        } else {
+          Q = getQb(from, action);
+          mQ = getQ(to, argmaxQb(to));
+          delta = reward - rho + mQ - Q;
+          updateQ_tab(theta_b, alpha * delta);
+        }
+        mQ = -DBL_MAX;
+        for (int i = 0; i < c.n_actions; i++) {
+          double val = (getQ(from, i) + getQb(from, i)) / 2.0;
+          if (val > mQ) mQ = val;
+        }
+        double nQ = Q + alpha * delta;
+        if (nQ - mQ < 1e-7) rho += c.beta * (reward - rho + mQ - nQ);
+        return delta;
+      }
+      default: throw std::runtime_error("oracle: unknown algorithm");
     }
   }
   void HandleTerminal(int episode) {  // agent.cpp:103-109 + policy.cpp:79-82
     traces.decay(0.0f);
     alpha = std::max(c.alpha_floor, c.alpha_start * std::pow(c.omega, (double)episode));
     if (c.policy_type == RLM_POLICY_EPSILON_GREEDY) eps = eps_init * std::pow(eps_floor / eps_init, (double)episode / (long)c.eps_T);
+    if (c.policy_type == RLM_POLICY_BOLTZMANN) tau = tau_init * std::pow(tau_floor / tau_init, (double)episode / (long)c.tau_T);  // :119-122
   }
 
   // ---- the learner loop as a tick-driven state machine ----
@@ -1231,6 +1289,7 @@ int64_t lobo_total_steps(lobo_env* e) { return e->total_steps; }
 int64_t lobo_total_ticks(lobo_env* e) { return e->total_ticks; }
 int64_t lobo_sum_traces(lobo_env* e) { return e->sum_traces; }
 const double* lobo_theta(lobo_env* e, int table) { return table == 0 ? e->theta.data() : (e->theta_b.empty() ? nullptr : e->theta_b.data()); }
+double lobo_rho(lobo_env* e) { return e->rho; }
 void lobo_handle_terminal(lobo_env* e, int episode) { e->HandleTerminal(episode); }
 // next episode on a FRESH experiment::serial::Learner (never-populated States, serial.cpp:9-16): Intraday::Initialise
 // + rewound data.  (A Learner reused across episodes would carry a stale State over, src/main.cpp:48-58; that

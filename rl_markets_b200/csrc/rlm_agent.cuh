@@ -274,6 +274,18 @@ __device__ __noinline__ int policy_action(AgentD& e, const double* qa, const dou
   if (pt == RLM_POLICY_EPSILON_GREEDY) {
     if (mt_uniform_real(mt, e.mt_pol_idx) < D.eps) return (int)mt_uniform_int(mt, e.mt_pol_idx, (unsigned)P.n_actions);
   }
+  if (pt == RLM_POLICY_BOLTZMANN) {  // Boltzmann::Sample (policy.cpp:98-115); exp() is CUDA's, the reference's is glibc's
+    double pr[RLM_MAX_ACTIONS];
+    double z = 0.0;
+    for (int a = 0; a < P.n_actions; ++a) { pr[a] = exp(qs[a] / D.tau); z += pr[a]; }
+    double acc = 0.0;
+    const double r = mt_uniform_real(mt, e.mt_pol_idx);
+    for (int a = 0; a < P.n_actions; ++a) {
+      acc += pr[a] / z;
+      if (r < acc) return a;
+    }
+    return P.n_actions - 1;
+  }
   return greedy_sample(e, qs);
 }
 

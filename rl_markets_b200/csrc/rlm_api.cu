@@ -52,11 +52,18 @@ struct rlm_handle_s {
   int ready_cap = 0;  // ticks per run call the ready counters can hold
   int n_policies = 1;
   size_t env_bytes = 0;
-  rlm_tick_msg* d_stream = nullptr;
-  size_t stream_cap = 0;  // messages
+  // STREAM source: two device chunks; rlm_load_ticks fills the idle one on a copy stream while the kernels of
+  // earlier rlm_run_ticks calls still read the other (upload of chunk k+1 overlaps compute of chunk k)
+  rlm_tick_msg* d_stream[2] = {nullptr, nullptr};
+  size_t stream_cap[2] = {0, 0};  // messages
+  int stream_buf = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  bool consumed_valid[2] = {false, false};
   int stream_ticks = 0, stream_cursor = 0;
+  void* d_gather = nullptr; void* h_gather = nullptr; size_t gather_cap = 0;  // rlm_get_reward/actions/state staging
   long long launches = 0;
-  double alpha = 0, eps = 0;
+  double alpha = 0, eps = 0, tau = 1.0;
 };
 
 static const rlm_handle_s* g_params_owner = nullptr;
@@ -103,10 +110,12 @@ static int derive(rlm_handle_s* h) {
   if (c.n_envs <= 0) return fail(RLM_ERR_INVALID_ARGUMENT, "n_envs must be positive");
   if (c.n_tilings != RLM_N_TILINGS) return fail(RLM_ERR_UNSUPPORTED, "the B200 path maps tiling j to lane j: n_tilings must be 32");
   if (c.n_actions < 1 || c.n_actions > RLM_MAX_ACTIONS) return fail(RLM_ERR_UNSUPPORTED, "n_actions must be in 1..9 (Intraday::DoAction has 9 actions)");
-  if (c.algorithm != RLM_ALGO_Q_LEARN && c.algorithm != RLM_ALGO_SARSA && c.algorithm != RLM_ALGO_DOUBLE_Q_LEARN)
-    return fail(RLM_ERR_UNSUPPORTED, "algorithm not built yet: q_learn, sarsa, double_q_learn are (R-learning variants: SURVEY 8f)");
-  if (c.policy_type != RLM_POLICY_GREEDY && c.policy_type != RLM_POLICY_RANDOM && c.policy_type != RLM_POLICY_EPSILON_GREEDY)
-    return fail(RLM_ERR_UNSUPPORTED, "policy not built yet: greedy, random, epsilon_greedy are (boltzmann: SURVEY 8f)");
+  if (c.algorithm < RLM_ALGO_Q_LEARN || c.algorithm > RLM_ALGO_DOUBLE_R_LEARN)
+    return fail(RLM_ERR_INVALID_ARGUMENT, "Please specify a valid learning algorithm!");  // main.cpp:188-189
+  if (c.policy_type < RLM_POLICY_GREEDY || c.policy_type > RLM_POLICY_BOLTZMANN)
+    return fail(RLM_ERR_INVALID_ARGUMENT, "Please specify a valid policy!");  // main.cpp:164-165
+  if (c.shared_policy && c.algorithm >= RLM_ALGO_R_LEARN)
+    return fail(RLM_ERR_UNSUPPORTED, "shared_policy is defined for q_learn, sarsa and double_q_learn (rho of the R-learning agents is per agent)");
   if (c.memory_size < 1 || c.memory_size > 2147483647LL) return fail(RLM_ERR_INVALID_ARGUMENT, "memory_size must fit the reference's int tile index");
   if (c.n_state_vars < 4 || c.n_state_vars > RLM_N_STATE_MAX) return fail(RLM_ERR_INVALID_ARGUMENT, "state.variables needs 4..13 entries (State::populateFeatures splits at 3)");
   if (c.n_bands < 1 || c.n_bands > RLM_MAX_BANDS) return fail(RLM_ERR_INVALID_ARGUMENT, "bad venue table");
@@ -124,7 +133,8 @@ static int derive(rlm_handle_s* h) {
   p.tp_is_micro = (c.target_price_type == RLM_TP_YAML_MIDPRICE) ? 1 : 0;
   p.l2p_book = (c.target_price_type == RLM_TP_YAML_BOOK) ? 1 : 0;  // intraday.cpp:64
   p.order_size = c.order_size; p.source = c.source; p.shared_policy = c.shared_policy;
-  p.is_double = (c.algorithm == RLM_ALGO_DOUBLE_Q_LEARN) ? 1 : 0;
+  p.is_double = (c.algorithm == RLM_ALGO_DOUBLE_Q_LEARN || c.algorithm == RLM_ALGO_DOUBLE_R_LEARN) ? 1 : 0;
+  p.beta = c.beta;
   p.pos_lb = c.pos_lb; p.pos_ub = c.pos_ub; p.memory_size = c.memory_size;
   p.m_pow2 = ((c.memory_size & (c.memory_size - 1)) == 0) ? 1 : 0;
   p.m_magic = (unsigned long long)((((unsigned __int128)1) << 64) / (unsigned __int128)c.memory_size);
@@ -273,6 +283,7 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   // Agent ctor: alpha(alpha_start) (agent.cpp:25); EpsilonGreedy ctor: eps(eps) (policy.cpp:63, main.cpp:149-154)
   h->alpha = cfg->alpha_start;
   h->eps = (double)cfg->eps_init;
+  h->tau = (double)cfg->tau_init;  // Boltzmann ctor (policy.cpp:85-96, main.cpp:157-162)
   memset(&h->dyn, 0, sizeof(h->dyn));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaMalloc(&h->ptr.ready, (size_t)cfg->n_envs * 4));
@@ -320,7 +331,14 @@ int rlm_destroy(rlm_handle h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->ptr.env); cudaFree(h->ptr.theta); cudaFree(h->ptr.theta_b); cudaFree(h->ptr.dtheta);
   cudaFree(h->ptr.trace_f); cudaFree(h->ptr.trace_e); cudaFree(h->ptr.mt_pol); cudaFree(h->ptr.mt_agt);
-  cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters); cudaFree(h->d_stream);
+  cudaFree(h->ptr.records); cudaFree(h->ptr.record_count); cudaFree(h->ptr.counters);
+  cudaFree(h->d_gather); if (h->h_gather) cudaFreeHost(h->h_gather);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->d_stream[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
   cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count); cudaFree(h->ptr.occ);
   cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
   for (auto e : h->ev) cudaEventDestroy(e);
@@ -355,28 +373,55 @@ int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks) {
   if (h->cfg.source != RLM_SOURCE_STREAM) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was created with source = generator");
   CK(cudaSetDevice(h->cfg.device));
   size_t n = (size_t)n_ticks * h->cfg.n_envs;
-  if (n > h->stream_cap) {
-    CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_stream);
-    h->d_stream = nullptr;
-    CK(cudaMalloc(&h->d_stream, n * sizeof(rlm_tick_msg)));
-    h->stream_cap = n;
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+    }
   }
-  CK(cudaMemcpyAsync(h->d_stream, msgs, n * sizeof(rlm_tick_msg), cudaMemcpyHostToDevice, h->stream));
-  h->ptr.stream = h->d_stream;
+  const int nb = h->stream_buf ^ 1;
+  if (n > h->stream_cap[nb]) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    cudaFree(h->d_stream[nb]);
+    h->d_stream[nb] = nullptr; h->stream_cap[nb] = 0;
+    CK(cudaMalloc(&h->d_stream[nb], n * sizeof(rlm_tick_msg)));
+    h->stream_cap[nb] = n;
+    h->consumed_valid[nb] = false;
+  }
+  // the idle chunk may still be read by kernels of an earlier run call
+  if (h->consumed_valid[nb]) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[nb], 0));
+  CK(cudaMemcpyAsync(h->d_stream[nb], msgs, n * sizeof(rlm_tick_msg), cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaEventRecord(h->ev_copied[nb], h->copy_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_copied[nb], 0));
+  h->stream_buf = nb;
+  h->ptr.stream = h->d_stream[nb];
   h->stream_ticks = n_ticks;
   h->stream_cursor = 0;
   return RLM_OK;
 }
 
+static int run_ticks_impl(rlm_handle h, int32_t n_ticks);
+
 int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
   if (!h || n_ticks < 0) return fail(RLM_ERR_INVALID_ARGUMENT, "bad arguments");
   if (n_ticks == 0) return RLM_OK;
   CK(cudaSetDevice(h->cfg.device));
+  int rc = run_ticks_impl(h, n_ticks);
+  if (rc == RLM_OK && h->cfg.source == RLM_SOURCE_STREAM && h->copy_stream) {
+    // the chunk these launches read may be overwritten by the load after next
+    CK(cudaEventRecord(h->ev_consumed[h->stream_buf], h->stream));
+    h->consumed_valid[h->stream_buf] = true;
+  }
+  return rc;
+}
+
+static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
   int rc = upload_params(h);
   if (rc) return rc;
   DynParams d = h->dyn;
-  d.alpha = h->alpha; d.eps = h->eps; d.n_ticks = n_ticks;
+  d.alpha = h->alpha; d.eps = h->eps; d.tau = h->tau; d.n_ticks = n_ticks;
   if (h->cfg.source == RLM_SOURCE_STREAM) {
     if (h->stream_cursor + n_ticks > h->stream_ticks)
       return fail(RLM_ERR_END_OF_DATA, "rlm_run_ticks: not enough ticks loaded (performAction would return false, base.cpp:289)");
@@ -506,30 +551,41 @@ int rlm_get_stats(rlm_handle h, int32_t env0, int32_t n, rlm_env_stats* out) {
   return RLM_OK;
 }
 
+// packed column read-back: gather kernel -> pinned staging -> caller's buffer (B values over PCIe, not B headers)
+static int fetch_column(rlm_handle h, int what, void* out, size_t bytes) {
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = upload_params(h);
+  if (rc) return rc;
+  if (bytes > h->gather_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_gather); if (h->h_gather) cudaFreeHost(h->h_gather);
+    h->d_gather = nullptr; h->h_gather = nullptr; h->gather_cap = 0;
+    CK(cudaMalloc(&h->d_gather, bytes));
+    CK(cudaMallocHost(&h->h_gather, bytes));
+    h->gather_cap = bytes;
+  }
+  CK(rlm_launch_gather(h->ptr, h->cfg.n_envs, what, h->d_gather, h->stream));
+  CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_gather, bytes);
+  return RLM_OK;
+}
+
 int rlm_get_state(rlm_handle h, float* out) {
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
-  std::vector<EnvHdr> v;
-  int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
-  if (rc) return rc;
-  for (int i = 0; i < h->cfg.n_envs; ++i)
-    for (int k = 0; k < h->cfg.n_state_vars; ++k) out[(size_t)i * h->cfg.n_state_vars + k] = v[i].ag.from_vars[k];
-  return RLM_OK;
+  return fetch_column(h, 2, out, (size_t)h->cfg.n_envs * h->cfg.n_state_vars * sizeof(float));
 }
 int rlm_get_reward(rlm_handle h, double* out) {
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
-  std::vector<EnvHdr> v;
-  int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
-  if (rc) return rc;
-  for (int i = 0; i < h->cfg.n_envs; ++i) out[i] = v[i].ag.last_reward;
-  return RLM_OK;
+  return fetch_column(h, 0, out, (size_t)h->cfg.n_envs * sizeof(double));
+}
+int rlm_get_rho(rlm_handle h, double* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  return fetch_column(h, 3, out, (size_t)h->cfg.n_envs * sizeof(double));
 }
 int rlm_get_actions(rlm_handle h, int32_t* out) {
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
-  std::vector<EnvHdr> v;
-  int rc = fetch_hdrs(h, 0, h->cfg.n_envs, v);
-  if (rc) return rc;
-  for (int i = 0; i < h->cfg.n_envs; ++i) out[i] = v[i].last_action;
-  return RLM_OK;
+  return fetch_column(h, 1, out, (size_t)h->cfg.n_envs * sizeof(int32_t));
 }
 
 int rlm_handle_terminal(rlm_handle h, int32_t episode) {
@@ -543,6 +599,10 @@ int rlm_handle_terminal(rlm_handle h, int32_t episode) {
   if (c.policy_type == RLM_POLICY_EPSILON_GREEDY) {                                   // policy.cpp:79-82
     double e0 = (double)c.eps_init, ef = (double)c.eps_floor;
     h->eps = e0 * pow(ef / e0, (double)episode / (double)(long)c.eps_T);
+  }
+  if (c.policy_type == RLM_POLICY_BOLTZMANN) {                                        // policy.cpp:119-122
+    double t0 = (double)c.tau_init, tf = (double)c.tau_floor;
+    h->tau = t0 * pow(tf / t0, (double)episode / (double)(long)c.tau_T);
   }
   return RLM_OK;
 }
@@ -610,7 +670,7 @@ int rlm_shared_tick_accumulate(rlm_handle h) {
   int rc = upload_params(h);
   if (rc) return rc;
   DynParams d = h->dyn;
-  d.alpha = h->alpha; d.eps = h->eps; d.n_ticks = 1;
+  d.alpha = h->alpha; d.eps = h->eps; d.tau = h->tau; d.n_ticks = 1;
   if (h->cfg.source == RLM_SOURCE_STREAM && !h->in_run) {
     if (h->stream_cursor + 1 > h->stream_ticks) return fail(RLM_ERR_END_OF_DATA, "not enough ticks loaded");
     d.stream_off = h->stream_cursor; d.stream_ticks = h->stream_ticks;

@@ -122,6 +122,18 @@ __global__ void rlm_clear_traces_kernel(DevPtrs ptr) {
   e->ag.n_traces = 0;
 }
 
+// column read-back for rlm_get_reward / rlm_get_actions / rlm_get_state: one packed array instead of B headers
+__global__ void rlm_gather_kernel(DevPtrs ptr, int what, void* out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.n_envs) return;
+  const EnvHdr* e = (const EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
+  if (what == 0) ((double*)out)[b] = e->ag.last_reward;
+  else if (what == 1) ((int*)out)[b] = e->last_action;
+  else if (what == 3) ((double*)out)[b] = e->ag.rho;
+  else
+    for (int k = 0; k < P.n_state_vars; ++k) ((float*)out)[(size_t)b * P.n_state_vars + k] = e->ag.from_vars[k];
+}
+
 // ---------------------------------------------------------------------------------------------
 // parity record (include/rlm_record.h); lane 0 fills everything but the trace hash
 __device__ __noinline__ void fill_record(rlm_step_record* r, const EnvHdr& e, const AgentD& ag, unsigned long long thash) {
@@ -412,7 +424,8 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
 }
 
 // TD error + trace decision of Agent::HandleTransition (agent.cpp:86-101); lane 0.
-// out[0] = trace decay rate, out[1] = alpha*delta/N_TILINGS, out[2] = table (0 = A, 1 = B)
+// out[0] = trace decay rate, out[1] = alpha*delta/N_TILINGS, out[2] = table (0 = A, 1 = B);
+// R-learning agents also hand out[3] = Q(from, action) and out[4] = the bootstrap value to td_rho
 __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, const double* q_pre_b, unsigned long long* mt_pol,
                                          unsigned long long* mt_agt, const DynParams& D, double* out) {
   const int action = ag.cur_action;
@@ -432,7 +445,7 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
     double Q = ag.q_from[action];
     int am2 = argmax_ties(ag, q_pre_a);
     delta = reward + F_term + P.gamma * q_pre_a[am2] - Q;
-  } else {  // DoubleQLearn :319-353
+  } else if (P.algorithm == RLM_ALGO_DOUBLE_Q_LEARN) {  // DoubleQLearn :319-353
     int amax = argmax_ties(ag, ag.q_from);
     if (action != amax) rate = 0.0f;
     if (mt_uniform_real(mt_agt, ag.mt_agt_idx) > 0.5) {
@@ -446,11 +459,59 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
       delta = reward + F_term + P.gamma * q_pre_a[am2] - Qb;
       table = 1;
     }
+  } else if (P.algorithm == RLM_ALGO_R_LEARN) {  // RLearn :364-380
+    int amax = argmax_ties(ag, ag.q_from);
+    if (action != amax) rate = 0.0f;
+    double Q = ag.q_from[action];
+    double mQ = q_pre_a[argmax_ties(ag, q_pre_a)];
+    delta = reward - ag.rho + mQ - Q;
+    out[3] = Q; out[4] = mQ;
+  } else if (P.algorithm == RLM_ALGO_ONLINE_R_LEARN) {  // Agent::UpdateTraces :111-115, OnlineRLearn :398-405
+    double Q = ag.q_from[action];
+    double gQ = q_pre_a[policy_action(ag, q_pre_a, q_pre_b, mt_pol, D)];
+    delta = reward - ag.rho + gQ - Q;
+    out[3] = Q; out[4] = gQ;
+  } else {  // DoubleRLearn :422-451
+    int amax = argmax_ties(ag, ag.q_from);
+    if (action != amax) rate = 0.0f;
+    double Q, mQ;
+    if (mt_uniform_real(mt_agt, ag.mt_agt_idx) > 0.5) {
+      Q = ag.q_from[action];
+      mQ = q_pre_b[argmax_ties(ag, q_pre_a)];
+      table = 0;
+    } else {
+      Q = ag.qb_from[action];
+      mQ = q_pre_a[argmax_ties(ag, q_pre_b)];
+      table = 1;
+    }
+    delta = reward - ag.rho + mQ - Q;
+    out[3] = Q; out[4] = mQ;
   }
   ag.last_delta = delta;
   out[0] = (double)rate;
   out[1] = (D.alpha * delta) / (double)RLM_N_TILINGS;  // Agent::updateQ: update / N_TILINGS
   out[2] = (double)table;
+}
+
+// Second half of the R-learning agents' UpdateWeights (agent.cpp:382-386,407-411,453-465): rho moves when the
+// updated Q(from, action) is (within 1e-7 of) the best value of the from-state under the UPDATED theta.
+// q_post_a/b = Q_A/Q_B(from, .) after updateQ; lane 0.
+__device__ __noinline__ void td_rho(AgentD& ag, const double* q_post_a, const double* q_post_b, const DynParams& D, const double* dec) {
+  const double Q = dec[3];
+  double boot = dec[4];
+  const double nQ = Q + D.alpha * ag.last_delta;
+  double best;
+  if (P.algorithm == RLM_ALGO_DOUBLE_R_LEARN) {
+    best = -1.7976931348623157e308;  // -DBL_MAX
+    for (int i = 0; i < P.n_actions; i++) {
+      double val = (q_post_a[i] + q_post_b[i]) / 2.0;
+      if (val > best) best = val;
+    }
+    boot = best;  // agent.cpp:453-464 reuses `mQ` for the maximum, so the rho target is built from it
+  } else {
+    best = q_post_a[argmax_ties(ag, q_post_a)];  // maxQ(from_state), agent.cpp:171-174
+  }
+  if (nQ - best < 1e-7) ag.rho += P.beta * (ag.last_reward - ag.rho + boot - nQ);
 }
 
 // The learner step of one ready env, by one warp.  `ag` / `scratch` are this warp's shared memory.
@@ -557,6 +618,19 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
         ptr.record_count[env] = c + 1;
       }
     }
+    const bool r_learning = P.algorithm >= RLM_ALGO_R_LEARN;
+    if (r_learning) {  // maxQ(from_state) under the updated theta, then rho (td_rho)
+      double d3 = 0.0, d4 = 0.0;
+      if (lane == 0) { d3 = dec[3]; d4 = dec[4]; }  // dec aliases vbuf, which the evaluation below reuses
+      __syncwarp();
+      unsigned long long bases_f[3];
+      double qa, qb;
+      eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, ag.null_from != 0, vbuf, lane, qa, qb, bases_f, false, idxc, occ);
+      if (lane < A) { q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
+      __syncwarp();
+      if (lane == 0) { double dd[5] = {0.0, 0.0, 0.0, d3, d4}; td_rho(ag, q_pre_a, q_pre_b, D, dd); }
+      __syncwarp();
+    }
     if (stage == 0) {
       // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
       if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
@@ -565,7 +639,8 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       __syncwarp();
       {
         double qa, qb;
-        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, true, idxc, occ);
+        // (the R-learning agents' extra evaluation overwrote the cached indices of the to-state)
+        eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, !r_learning, idxc, occ);
         if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       }
       steps_done++;
@@ -588,8 +663,8 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
 #define A3_WARPS 3
 #define A3_Q 0                                             // q_pre_a, q_pre_b: 18 doubles
 #define A3_SS (A3_Q + 8 * 2 * RLM_MAX_ACTIONS)             // small set
-#define A3_DEC (A3_SS + 4 * SS_SLOTS)                      // 4 doubles
-#define A3_V (A3_DEC + 32)                                 // V[table][g][a][VROW]
+#define A3_DEC (A3_SS + 4 * SS_SLOTS)                      // 6 doubles
+#define A3_V (A3_DEC + 48)                                 // V[table][g][a][VROW]
 size_t rlm_agent3_smem_bytes(int is_double) {
   return AG_BYTES + (((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 3 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
 }
@@ -638,6 +713,24 @@ __device__ __forceinline__ void a3_sums(const double* V, bool has_b, int lane, d
     qa = seg_sum(qa, w, V + ((size_t)g * RLM_MAX_ACTIONS + lane) * VROW);
     if (has_b) qb = seg_sum(qb, w, V + ((size_t)(3 + g) * RLM_MAX_ACTIONS + lane) * VROW);
   }
+}
+
+// R-learning agents (whole CTA): maxQ(from_state) under the UPDATED theta, then the rho update (td_rho).
+// Kept out of line so that its index registers do not weigh on the Q-learning / SARSA path.
+__device__ __noinline__ void a3_rho_step(AgentD& ag, const double* theta_a, const double* theta_b, const unsigned* occ, double* V,
+                                         double* q_post_a, double* q_post_b, const double* dec, const DynParams& D, int warp, int lane) {
+  const int A = P.n_actions;
+  __syncthreads();  // trace pass done, V free
+  int f2[RLM_MAX_ACTIONS];
+  a3_hash(rlm_rndseq_table, ag.from_vars, P.n_state_vars, ag.null_from != 0, warp, lane, f2);
+  a3_gather(theta_a, theta_b, occ, f2, warp, lane, V);
+  __syncthreads();
+  if (warp == 0) {
+    if (lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_post_a[lane] = qa; q_post_b[lane] = qb; }
+    __syncwarp();
+    if (lane == 0) td_rho(ag, q_post_a, q_post_b, D, dec);
+  }
+  __syncthreads();  // every warp has read from_vars
 }
 
 __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
@@ -738,12 +831,13 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
             ptr.record_count[env] = c + 1;
           }
         }
-        if (stage == 0) {
-          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
-          ag.from_base0[lane] = mod_m(base);
-          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
-          steps_done++;
-        }
+      }
+      if (P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, V, q_pre_a, q_pre_b, dec, D, warp, lane);
+      if (warp == 0 && stage == 0) {
+        if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+        ag.from_base0[lane] = mod_m(base);
+        if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+        steps_done++;
       }
       if (stage == 0) {  // Q(from = to-state, .) under the UPDATED theta (serial.cpp:55,60); indices are still in registers
         __syncthreads();
@@ -1156,6 +1250,10 @@ cudaError_t rlm_launch_seed(const DevPtrs& ptr, int n_envs, unsigned seed, cudaS
 }
 cudaError_t rlm_launch_random_init(const DevPtrs& ptr, int n_policies, cudaStream_t st) {
   rlm_random_init_kernel<<<(n_policies + 63) / 64, 64, 0, st>>>(ptr, n_policies);
+  return cudaGetLastError();
+}
+cudaError_t rlm_launch_gather(const DevPtrs& ptr, int n_envs, int what, void* out, cudaStream_t st) {
+  rlm_gather_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(ptr, what, out);
   return cudaGetLastError();
 }
 cudaError_t rlm_launch_clear_traces(const DevPtrs& ptr, int n_envs, cudaStream_t st) {

@@ -64,7 +64,8 @@ struct alignas(16) AgentD {
   int kind;        // why the env is in the ready list: 0 learner step, 1 end of warm-up
   int ep_step, err;
   int n_occ;   // independent policies: bits set in this env's occupancy bitmap; > M/4 => treat theta as dense
-  int pad[3];
+  double rho;  // R-learning average reward (agent.h:131,145,157); lives as long as theta does
+  int pad;
 };
 
 struct EnvHdr {
@@ -104,7 +105,7 @@ struct DevParams {
   int m_pow2;
   int ra_m[RLM_MAX_ACTIONS];  // rndseq[(a + 449*4) & 2047] mod M: the action term of a group-0 tile hash
   float gl;  // (float)(gamma*lambda): Traces::decay(float rate)
-  double gw[3], gamma;
+  double gw[3], gamma, beta;
   float damping, pos_weight, trd_weight, pnl_weight;
   double ewma_alpha;
   int win_size[RLM_NWIN], win_off[RLM_NWIN];
@@ -119,7 +120,7 @@ struct DevParams {
 };
 
 struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
-  double alpha, eps;
+  double alpha, eps, tau;
   int greedy;
   int n_ticks;
   int stream_ticks;   // ticks in the resident stream chunk

@@ -67,6 +67,8 @@ def lib():
         L.lobo_handle_terminal.argtypes = [C.c_void_p, C.c_int]
         L.lobo_go_greedy.argtypes = [C.c_void_p]
         L.lobo_reset.argtypes = [C.c_void_p]
+        L.lobo_rho.argtypes = [C.c_void_p]
+        L.lobo_rho.restype = C.c_double
         L.lobo_run_batch.restype = C.c_int64
         L.lobo_run_batch.argtypes = [C.POINTER(abi.Config), C.c_int32, C.c_int64, C.c_int32,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -124,7 +126,7 @@ def run_port(cfg, env_index, ticks, max_steps=-1, rec_cap=None):
     st = abi.EnvStats()
     L.lobo_stats(h, C.byref(st))
     out = {"records": [recs[i] for i in range(min(steps, cap))], "steps": steps, "consumed": used.value, "stats": st,
-           "sum_traces": L.lobo_sum_traces(h), "ticks": L.lobo_total_ticks(h), "_keep": recs}
+           "sum_traces": L.lobo_sum_traces(h), "ticks": L.lobo_total_ticks(h), "rho": L.lobo_rho(h), "_keep": recs}
     M = cfg.memory_size
     th = L.lobo_theta(h, 0)
     out["theta"] = [th[i] for i in range(M)] if M <= (1 << 20) else None

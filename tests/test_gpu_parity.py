@@ -40,15 +40,26 @@ def _compare_env(rlm_records, port, label):
     return n
 
 
-@pytest.mark.parametrize("algo,M", [("q_learn", 65536), ("sarsa", 16384), ("double_q_learn", 65536), ("q_learn", 4096)])
-def test_generator_mode_matches_oracle(rlm, oracle, algo, M):
+_BOLTZ = {"policy.type": "boltzmann", "policy.tau_init": 0.1, "policy.tau_floor": 0.01, "policy.tau_T": 10}
+
+
+@pytest.mark.parametrize("algo,M,over", [
+    ("q_learn", 65536, {}), ("sarsa", 16384, {}), ("double_q_learn", 65536, {}), ("q_learn", 4096, {}),
+    # R-learning agents (agent.cpp:357-467) and the Boltzmann policy (policy.cpp:85-122; libm exp on the CPU side,
+    # CUDA exp here: an action can differ only if a uniform draw lands within an ulp of a cumulative probability)
+    ("r_learn", 16384, {"policy.eps_init": 0.3}), ("online_r_learn", 16384, {"policy.eps_init": 0.3}),
+    ("double_r_learn", 8209, {"policy.eps_init": 0.3, "learning.alpha_start": 0.01}),
+    ("q_learn", 8192, _BOLTZ), ("double_r_learn", 4096, dict(_BOLTZ, **{"learning.alpha_start": 0.01})),
+])
+def test_generator_mode_matches_oracle(rlm, oracle, algo, M, over):
     n_envs, n_ticks = 8, 3000
-    y, cfg = _mk(algo, M, n_envs, flow_seed=11, rec_cap=1500)
+    y, cfg = _mk(algo, M, n_envs, flow_seed=11, rec_cap=1500, **over)
     m = rlm.BatchedMarket(cfg)
     m.run_ticks(1000)
     m.run_ticks(2000)  # chunked launches must not change anything
     m.sync()
     cnt = m.counters()
+    rew, act, st, rho = m.rewards(), m.actions(), m.state(), m.rho()
     total = 0
     for b in range(n_envs):
         ticks = oracle.generate_ticks(cfg, b, n_ticks)
@@ -56,8 +67,13 @@ def test_generator_mode_matches_oracle(rlm, oracle, algo, M):
         recs, keep = m.records(b)
         assert len(recs) == port["steps"], "env %d: step count cuda %d oracle %d" % (b, len(recs), port["steps"])
         total += _compare_env(recs, port, "%s env %d" % (algo, b))
+        # packed column getters (env.getReward / state->toVector of the last completed step)
+        last = recs[-1]
+        assert C.c_double(rew[b]).value == last.reward and 0 <= act[b] < cfg.n_actions
+        assert list(st[b * cfg.n_state_vars:(b + 1) * cfg.n_state_vars]) == list(last.state[:cfg.n_state_vars])
         th = m.theta(b, 0)
         assert bytes(th) == bytes((C.c_double * M)(*port["theta"])), "%s env %d: theta differs" % (algo, b)
+        assert rho[b] == port["rho"] and (port["rho"] != 0.0) == (algo.endswith("r_learn")), (algo, b, rho[b], port["rho"])
     assert cnt.steps == total
     assert cnt.ticks == sum([n_ticks - 1] * n_envs)  # the first row only opens the market (intraday.cpp:111-116)
     m.close()
@@ -72,9 +88,16 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
         for t in range(n_ticks):
             msgs[t * n_envs + b] = one[t]
     ms = rlm.BatchedMarket(cfg)
-    ms.load_ticks(msgs, n_ticks)
-    ms.run_ticks(700)
-    ms.run_ticks(800)
+    # three chunks, uploads pipelined against the running kernels (rlm_load_ticks double-buffers):
+    # load(k+1) is issued while run(k) is still executing, without any host sync in between
+    base, per_tick = C.addressof(msgs), n_envs * C.sizeof(abi.TickMsg)
+    ms.load_ticks(base, 500)
+    ms.run_ticks(200)
+    ms.run_ticks(300)
+    ms.load_ticks(base + 500 * per_tick, 500)
+    ms.run_ticks(500)
+    ms.load_ticks(base + 1000 * per_tick, 500)
+    ms.run_ticks(500)
     ms.sync()
     y2, cfg2 = _mk("q_learn", 8192, n_envs, flow_seed=5, rec_cap=800, source=abi.SOURCE_GENERATOR)
     mg = rlm.BatchedMarket(cfg2)
@@ -92,3 +115,29 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
     assert ei.value.code == abi.RLM_ERR_END_OF_DATA
     ms.close()
     mg.close()
+
+
+@pytest.mark.parametrize("env_vars,algo", [
+    ({"RLM_ENV_VARIANT": "1"}, "q_learn"),        # thread-per-env tick kernel (default for B > 16384)
+    ({"RLM_AGENT_VARIANT": "1"}, "q_learn"),      # one-warp-per-env learner kernel
+    ({"RLM_AGENT_VARIANT": "1"}, "double_r_learn"),
+    ({"RLM_ENGINE": "p"}, "sarsa"),               # persistent queue engine
+    ({"RLM_ENGINE": "f"}, "double_q_learn"),      # fused warp-per-env engine
+    ({"RLM_ENGINE": "f"}, "r_learn"),
+])
+def test_every_engine_variant_matches_oracle(rlm, oracle, monkeypatch, env_vars, algo):
+    """The non-default kernels (selected by environment variables read in rlm_create) are held to the same bar."""
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, v)
+    n_envs, n_ticks, M = 5, 1500, 8192
+    y, cfg = _mk(algo, M, n_envs, flow_seed=23, rec_cap=800)
+    m = rlm.BatchedMarket(cfg)
+    m.run_ticks(n_ticks)
+    m.sync()
+    for b in range(n_envs):
+        port = oracle.run_port(cfg, b, oracle.generate_ticks(cfg, b, n_ticks))
+        recs, _keep = m.records(b)
+        assert len(recs) == port["steps"] > 100
+        _compare_env(recs, port, "%s %r env %d" % (algo, env_vars, b))
+        assert bytes(m.theta(b, 0)) == bytes((C.c_double * M)(*port["theta"]))
+    m.close()

@@ -63,6 +63,13 @@ def test_unsupported_configs_fail_loudly(rlm):
         rlm.BatchedMarket(c)
     assert ei.value.code == abi.RLM_ERR_UNSUPPORTED
     c = _cfg(4)
-    c.policy_type = abi.POLICY["boltzmann"]
-    with pytest.raises(rlm.RlmError):
+    c.policy_type = 7  # main.cpp:164-165 "Please specify a valid policy!"
+    with pytest.raises(rlm.RlmError) as ei:
         rlm.BatchedMarket(c)
+    assert ei.value.code == abi.RLM_ERR_INVALID_ARGUMENT
+    c = _cfg(4)
+    c.algorithm = abi.ALGO["r_learn"]  # rho is per agent: no shared-policy formulation
+    c.shared_policy = 1
+    with pytest.raises(rlm.RlmError) as ei:
+        rlm.BatchedMarket(c)
+    assert ei.value.code == abi.RLM_ERR_UNSUPPORTED

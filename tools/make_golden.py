@@ -29,6 +29,14 @@ CASES = [
          over={"policy.eps_init": 0.05}),
     dict(name="q_learn_m4096_random_init", algo="q_learn", M=4096, flow_seed=13, env=5, ticks=2500,
          over={"learning.random_init": True, "debug.random_seed": 77}),
+    # R-learning agents (agent.cpp:357-467) and the Boltzmann policy (policy.cpp:85-122)
+    dict(name="r_learn_m16384", algo="r_learn", M=16384, flow_seed=15, env=6, ticks=2500, over={"policy.eps_init": 0.3}),
+    dict(name="online_r_learn_m16384", algo="online_r_learn", M=16384, flow_seed=15, env=7, ticks=2500,
+         over={"policy.eps_init": 0.3}),
+    dict(name="double_r_learn_m8209", algo="double_r_learn", M=8209, flow_seed=17, env=8, ticks=2500,
+         over={"policy.eps_init": 0.3, "learning.alpha_start": 0.01}),
+    dict(name="sarsa_boltzmann_m8192", algo="sarsa", M=8192, flow_seed=19, env=9, ticks=2500,
+         over={"policy.type": "boltzmann", "policy.tau_init": 0.05, "policy.tau_floor": 0.01, "policy.tau_T": 10}),
 ]
 
 
