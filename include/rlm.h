@@ -158,6 +158,19 @@ int rlm_destroy(rlm_handle h);
 /* Intraday::Initialise for every env: books/windows cleared, stream rewound. */
 int rlm_reset(rlm_handle h);
 
+/* Which experiment::serial step the handle runs (src/experiment/serial.cpp):
+ *   RLM_MODE_TRAIN    Learner::_step    :53-70   act on the previous state, performAction, newState, HandleTransition
+ *   RLM_MODE_BACKTEST Backtester::_step :121-137 newState, act, performAction; theta and traces are never touched.
+ * In backtest mode rlm_read_records yields one row per step with every column of Intraday::LogProfit's profit_log
+ * (intraday.cpp:437-451) and rlm_get_stats the counters Base::writeStats dumps (base.cpp:451-456). */
+enum { RLM_MODE_TRAIN = 0, RLM_MODE_BACKTEST = 1 };
+int rlm_set_mode(rlm_handle h, int32_t mode);
+
+/* `environment::Intraday<> env(c)` of src/main.cpp:219: every env object is rebuilt from scratch (window sums,
+ * statistics, position, book, records) while the agents keep theta, traces, generator positions and schedules.
+ * `flow` (may be NULL = keep) replaces the synthetic-flow parameters, i.e. "LoadData of another day". */
+int rlm_new_env(rlm_handle h, const rlm_flow_params* flow);
+
 /* RLM_SOURCE_STREAM: append `n_ticks` messages per env, host layout msgs[t][env] (tick-major).
  * The copy is issued on the handle's copy stream; the buffer must stay valid until rlm_sync. */
 int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks);

@@ -51,6 +51,10 @@ typedef struct rlm_step_record {
   double ep_pnl;         /* episode_stats.pnl  (cash)            [bit-exact]    */
   double ep_reward;      /* episode_stats.reward                                */
   double ep_bandh;       /* episode_stats.bandh                                 */
+  /* the remaining columns of Intraday::LogProfit's profit_log row (intraday.cpp:437-451) */
+  double midprice;       /* midprice(ask_book_, bid_book_) after the step       */
+  double spread;         /* spread(ask_book_, bid_book_) after the step         */
+  double bandh_step;     /* agg_mpm of performAction (base.cpp:285-333)         */
   rlm_order_rec ask;     /* agent ask order after the step                      */
   rlm_order_rec bid;
   int32_t ask_transactions; /* AskBook::n_transacted()           [bit-exact]    */
@@ -59,7 +63,8 @@ typedef struct rlm_step_record {
   int32_t market_sells;
   int32_t lo_vol_step;   /* Base::lo_vol_step                                   */
   int32_t n_state;       /* number of state variables                           */
-  float state[RLM_N_STATE_MAX + 1]; /* to-state variables (Intraday::getState)  */
+  float state[RLM_N_STATE_MAX + 1]; /* to-state variables (Intraday::getState); backtest mode: the state
+                            the action was chosen from (Backtester::_step, serial.cpp:126-128) */
   double delta;          /* TD error returned by UpdateWeights   [tol 1e-5]     */
   int32_t n_traces;      /* Traces::n_nonzero_traces after the update           */
   int32_t pad;

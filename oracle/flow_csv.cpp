@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
   uint64_t env = 0;
   long n_ticks = 1000;
   int dt_ms = 250;
+  long t0_ms = -1;
   std::string md, tas, packed;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -37,13 +38,15 @@ int main(int argc, char** argv) {
     else if (a == "--env") env = strtoull(next(), 0, 10);
     else if (a == "--ticks") n_ticks = atol(next());
     else if (a == "--dt-ms") dt_ms = atoi(next());
+    else if (a == "--t0-ms") t0_ms = atol(next());
     else if (a == "--md") md = next();
     else if (a == "--tas") tas = next();
     else if (a == "--packed") packed = next();
-    else { fprintf(stderr, "usage: flow_csv --seed S --env B --ticks N [--dt-ms D] [--md f] [--tas f] [--packed f]\n"); return 2; }
+    else { fprintf(stderr, "usage: flow_csv --seed S --env B --ticks N [--dt-ms D] [--t0-ms T] [--md f] [--tas f] [--packed f]\n"); return 2; }
   }
   rlm_flow_params p;
   rlm_flow_default_params(&p, seed, dt_ms);
+  if (t0_ms >= 0) p.t0_ms = (int32_t)t0_ms;
   rlm_flow_state s;
   rlm_flow_init(&s, &p, env);
 

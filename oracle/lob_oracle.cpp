@@ -668,6 +668,7 @@ struct lobo_env {
   double tau = 0, tau_init = 0, tau_floor = 0;  // Boltzmann (policy.cpp:85-96; read as float, main.cpp:157-158)
   double rho = 0.0;                             // R-learning average reward (agent.h:131,145,157)
   bool greedy = false;
+  bool backtest = false;  // Backtester::_step instead of Learner::_step (serial.cpp:121-137)
   MT64 policy_gen, agent_gen;
   GlibcRand crand;
   // bookkeeping
@@ -715,6 +716,22 @@ struct lobo_env {
     state2.init(c.memory_size, c.n_actions, c.n_tilings);
     state = &state1; last_state = &state2;  // serial.cpp:14-15
     reset_episode();
+  }
+
+  // `environment::Intraday<> env(c)` of main.cpp:219: a NEW env object (window sums, statistics, target price,
+  // position all start from scratch) driven by the SAME agent (theta, traces, generators, schedules)
+  void new_env() {
+    lobo_env* f = new lobo_env();
+    f->sh_a = sh_a; f->sh_b = sh_b; f->sh_da = sh_da; f->sh_db = sh_db;
+    f->init(&c, env_index);
+    f->theta.swap(theta); f->theta_b.swap(theta_b);
+    f->traces = traces;
+    f->policy_gen = policy_gen; f->agent_gen = agent_gen; f->crand = crand;
+    f->alpha = alpha; f->eps = eps; f->tau = tau; f->rho = rho; f->greedy = greedy; f->backtest = backtest;
+    f->total_steps = total_steps; f->total_ticks = total_ticks; f->sum_traces = sum_traces;
+    *this = *f;
+    state = &state1; last_state = &state2;
+    delete f;
   }
 
   // Base::Initialise base.cpp:123-135 + Intraday::Initialise intraday.cpp:105-109
@@ -1105,9 +1122,15 @@ struct lobo_env {
   // begin of Learner::_step (serial.cpp:55-61) up to the first NextState of performAction
   // (base.cpp:254-284).  Returns false when the episode is over.
   bool begin_step() {
-    std::swap(state, last_state);
-    if (isTerminal()) { finish_episode(); return false; }
-    cur_action = (int)agent_action(*last_state);
+    if (backtest) {  // Backtester::_step serial.cpp:121-128: no swap, the state is rebuilt from the env
+      if (isTerminal()) { finish_episode(); return false; }
+      newState(state);
+      cur_action = (int)agent_action(*state);
+    } else {
+      std::swap(state, last_state);
+      if (isTerminal()) { finish_episode(); return false; }
+      cur_action = (int)agent_action(*last_state);
+    }
     last_action = cur_action;
     lo_vol_step = 0;
     pnl_step = 0.0;
@@ -1145,6 +1168,13 @@ struct lobo_env {
     episode_stats.reward += agg_r; experiment_stats.reward += agg_r;
     experiment_stats.pnl += agg_pnl;
     episode_stats.bandh += agg_mpm; experiment_stats.bandh += agg_mpm;
+    if (backtest) {  // no newState / HandleTransition after performAction (serial.cpp:130-136)
+      double reward = getReward();
+      last_reward = reward; last_delta = 0.0;
+      if (rec) fill_record(rec, reward, 0.0);
+      total_steps++; ep_step++;
+      return;
+    }
     newState(state);
     double reward = getReward();
     // Agent::HandleTransition agent.cpp:86-101
@@ -1170,6 +1200,7 @@ struct lobo_env {
     r->ask_level = ask_level; r->bid_level = bid_level;
     r->reward = reward; r->pnl_step = pnl_step;
     r->ep_pnl = episode_stats.pnl; r->ep_reward = episode_stats.reward; r->ep_bandh = episode_stats.bandh;
+    r->midprice = m_midprice(ask, bid); r->spread = m_spread(ask, bid); r->bandh_step = agg_mpm;  // intraday.cpp:437-451
     fill_order(ask, r->ask); fill_order(bid, r->bid);
     r->ask_transactions = ask.n_transacted_; r->bid_transactions = bid.n_transacted_;
     r->market_buys = trade_stats.market_buys; r->market_sells = trade_stats.market_sells;
@@ -1301,6 +1332,8 @@ void lobo_reset(lobo_env* e) {
   e->reset_episode();
 }
 void lobo_go_greedy(lobo_env* e) { e->greedy = true; }
+void lobo_set_backtest(lobo_env* e, int on) { e->backtest = on != 0; }
+void lobo_new_env(lobo_env* e) { e->new_env(); }
 
 int64_t lobo_run_batch(const rlm_config* cfg, int32_t n_envs, int64_t n_ticks, int32_t n_threads, int64_t* total_ticks,
                        double* seconds) {

@@ -45,6 +45,8 @@ const double* lobo_theta(lobo_env* e, int table);
 void lobo_handle_terminal(lobo_env* e, int episode);
 void lobo_go_greedy(lobo_env* e);
 void lobo_reset(lobo_env* e);
+void lobo_set_backtest(lobo_env* e, int on);
+void lobo_new_env(lobo_env* e);
 double lobo_rho(lobo_env* e);
 
 /* Run n_envs independent envs (env_index0 + b), each for `n_ticks` generated ticks, on

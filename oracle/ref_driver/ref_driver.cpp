@@ -33,6 +33,7 @@
 #include "rl/state.h"
 #include "environment/intraday.h"
 #include "market/market.h"
+#include "market/measures.h"
 
 #include "rlm_record.h"
 
@@ -55,6 +56,9 @@ struct EnvSpy : public environment::Intraday<> {
     r.ep_pnl = episode_stats.pnl;
     r.ep_reward = episode_stats.reward;
     r.ep_bandh = episode_stats.bandh;
+    r.midprice = market::measure::midprice(ask_book_, bid_book_);
+    r.spread = market::measure::spread(ask_book_, bid_book_);
+    r.bandh_step = last_bandh;
     fill_order(ask_book_, r.ask);
     fill_order(bid_book_, r.bid);
     r.ask_transactions = ask_book_.n_transacted();
@@ -78,6 +82,13 @@ struct EnvSpy : public environment::Intraday<> {
   }
 
   long n_ticks_total() { return tick_stats.total_ticks; }
+
+  // the bandh_step column of the profit_log row (a local of performAction, base.cpp:333)
+  double last_bandh = 0.0;
+  void LogProfit(int action, double pnl, double bandh) override {
+    last_bandh = bandh;
+    environment::Intraday<>::LogProfit(action, pnl, bandh);
+  }
 };
 
 // Captures delta and exposes theta / traces of any concrete agent.
@@ -130,13 +141,14 @@ void usage() {
   fprintf(stderr,
           "usage: ref_driver --config cfg.yaml --symbol AAL.L --md md.csv --tas tas.csv\n"
           "                  [--algo q_learn|sarsa|double_q_learn] [--steps N] [--dump out.bin]\n"
-          "                  [--theta out_theta.bin] [--quiet]\n");
+          "                  [--theta out_theta.bin] [--quiet]\n"
+          "                  [--test-md md.csv --test-tas tas.csv --dump-test out.bin]   evaluation phase of main.cpp:216-241\n");
 }
 
 }  // namespace
 
 int main(int argc, char** argv) {
-  string cfg, symbol = "AAL.L", md, tas, algo, dump, theta_out;
+  string cfg, symbol = "AAL.L", md, tas, algo, dump, theta_out, test_md, test_tas, dump_test;
   long max_steps = -1;
   bool quiet = false;
   for (int i = 1; i < argc; ++i) {
@@ -150,6 +162,9 @@ int main(int argc, char** argv) {
     else if (a == "--steps") max_steps = atol(next().c_str());
     else if (a == "--dump") dump = next();
     else if (a == "--theta") theta_out = next();
+    else if (a == "--test-md") test_md = next();
+    else if (a == "--test-tas") test_tas = next();
+    else if (a == "--dump-test") dump_test = next();
     else if (a == "--quiet") quiet = true;
     else { usage(); return 2; }
   }
@@ -266,6 +281,44 @@ int main(int argc, char** argv) {
     double secs = chrono::duration<double>(t_end - t_start).count();
     if (fd) fclose(fd);
 
+    // Evaluation phase, main.cpp:216-241: greedy agent, a NEW Intraday object, Backtester::RunEpisode
+    // (Runner::RunEpisode serial.cpp:18-34 + Backtester::_step serial.cpp:121-137).
+    long test_steps = 0;
+    rlm_step_record test_last;
+    memset(&test_last, 0, sizeof(test_last));
+    if (!test_md.empty()) {
+      m->GoGreedy();
+      EnvSpy env2(c);
+      env2.LoadData(symbol, test_md, test_tas);
+      rl::State b1(c), b2(c);  // Runner ctor, serial.cpp:9-16
+      rl::State* bstate = &b1;
+      rl::State* blast = &b2;
+      FILE* ft2 = dump_test.empty() ? nullptr : fopen(dump_test.c_str(), "wb");
+      if (!env2.Initialise()) throw runtime_error("Initialise() failed on the test data");
+      blast->newState(env2);
+      while (true) {
+        if (env2.isTerminal()) break;
+        bstate->newState(env2);
+        int action = m->action(*bstate);
+        if (!env2.performAction(action)) break;
+        rlm_step_record r;
+        memset(&r, 0, sizeof(r));
+        r.step = (int32_t)test_steps;
+        r.action = action;
+        env2.fill(r);
+        r.reward = env2.getReward();
+        auto& sv = bstate->toVector();
+        r.n_state = (int32_t)sv.size();
+        for (size_t i = 0; i < sv.size() && i < RLM_N_STATE_MAX; ++i) r.state[i] = sv[i];
+        r.n_traces = av.traces()->n_nonzero_traces;
+        if (ft2) fwrite(&r, sizeof(r), 1, ft2);
+        ++test_steps;
+      }
+      env2.ClearInventory();
+      env2.fill(test_last);
+      if (ft2) fclose(ft2);
+    }
+
     if (!theta_out.empty()) {
       // sparse dump: (int64 index, double value) for every nonzero weight of table A
       FILE* ft = fopen(theta_out.c_str(), "wb");
@@ -291,7 +344,10 @@ int main(int argc, char** argv) {
              steps, terminal ? 1 : 0, secs, steps / std::max(secs, 1e-12), r.time_ms, (long long)r.position,
              r.ep_pnl, r.ep_reward, sum_reward, r.ask_transactions, r.bid_transactions);
       for (unsigned a = 0; a < n_actions && a < 16; ++a) printf("%s%ld", a ? ", " : "", hist[a]);
-      printf("]}\n");
+      printf("], \"test_steps\": %ld, \"test_position\": %lld, \"test_ep_pnl\": %.17g, \"test_ep_reward\": %.17g, "
+             "\"test_ask_tx\": %d, \"test_bid_tx\": %d, \"test_market_buys\": %d, \"test_market_sells\": %d}\n",
+             test_steps, (long long)test_last.position, test_last.ep_pnl, test_last.ep_reward, test_last.ask_transactions,
+             test_last.bid_transactions, test_last.market_buys, test_last.market_sells);
     }
     delete m;
     return 0;

@@ -21,6 +21,7 @@ REWARD = {"none": 0, "pnl": 1, "pnl_damped": 2, "spread": 3, "normed": 4, "lovol
 VAR = {"pos": 0, "spd": 1, "mpm": 2, "imb": 3, "svl": 4, "vol": 5, "rsi": 6, "vwap": 7, "a_dist": 8,
        "a_queue": 9, "b_dist": 10, "b_queue": 11, "last_action": 12}
 TP_YAML = {"midprice": 0, "microprice": 1, "vwap": 2, "book": 3}
+MODE_TRAIN, MODE_BACKTEST = 0, 1
 SOURCE_GENERATOR, SOURCE_STREAM = 0, 1
 
 RLM_OK = 0
@@ -98,6 +99,9 @@ class StepRecord(C.Structure):
         ("ep_pnl", C.c_double),
         ("ep_reward", C.c_double),
         ("ep_bandh", C.c_double),
+        ("midprice", C.c_double),
+        ("spread", C.c_double),
+        ("bandh_step", C.c_double),
         ("ask", OrderRec),
         ("bid", OrderRec),
         ("ask_transactions", C.c_int32),

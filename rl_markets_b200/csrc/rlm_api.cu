@@ -211,7 +211,10 @@ static int derive(rlm_handle_s* h) {
 }
 
 static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tslot, int stage) {
-  if (h->agent_variant == 3) return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, tslot, h->n_sms, stage, h->stream);
+  if (h->agent_variant == 3) {
+    const int full = (d.backtest || h->cfg.algorithm >= RLM_ALGO_R_LEARN) ? 1 : 0;
+    return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, tslot, h->n_sms, stage, full, h->stream);
+  }
   return rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, tslot, h->n_sms, stage, h->stream);
 }
 
@@ -364,6 +367,32 @@ int rlm_reset(rlm_handle h) {
   int rc = upload_params(h);
   if (rc) return rc;
   CK(rlm_launch_init(h->ptr, h->cfg.n_envs, 1, h->stream));
+  h->stream_cursor = 0; h->stream_ticks = 0;
+  return RLM_OK;
+}
+
+int rlm_set_mode(rlm_handle h, int32_t mode) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  if (mode != RLM_MODE_TRAIN && mode != RLM_MODE_BACKTEST) return fail(RLM_ERR_INVALID_ARGUMENT, "unknown mode");
+  if (mode == RLM_MODE_BACKTEST && h->engine != 1) return fail(RLM_ERR_UNSUPPORTED, "backtest mode runs on the tick-synchronous engine only");
+  if (mode == RLM_MODE_BACKTEST && h->cfg.shared_policy) return fail(RLM_ERR_UNSUPPORTED, "backtest mode with shared_policy is not built");
+  h->dyn.backtest = mode;
+  return RLM_OK;
+}
+
+int rlm_new_env(rlm_handle h, const rlm_flow_params* flow) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  if (flow) {
+    CK(cudaStreamSynchronize(h->stream));  // running kernels read the old parameters from constant memory
+    h->cfg.flow = *flow;
+    h->hp.flow = *flow;
+    if (g_params_owner == h) g_params_owner = nullptr;  // force the re-upload
+  }
+  int rc = upload_params(h);
+  if (rc) return rc;
+  CK(rlm_launch_init(h->ptr, h->cfg.n_envs, 2, h->stream));
+  if (h->ptr.records) CK(cudaMemsetAsync(h->ptr.record_count, 0, (size_t)h->hp.record_envs * 4, h->stream));
   h->stream_cursor = 0; h->stream_ticks = 0;
   return RLM_OK;
 }

@@ -42,17 +42,23 @@ cudaError_t rlm_upload_params(const DevParams* p) { return cudaMemcpyToSymbol(P,
 
 // ---------------------------------------------------------------------------------------------
 // init: Intraday ctor/Initialise state + RNG seeding, one thread per env.
-// mode 0: full create; mode 1: episode reset (Base::Initialise base.cpp:123-135 keeps window sums, A13)
+// mode 0: full create; mode 1: episode reset (Base::Initialise base.cpp:123-135 keeps window sums, A13);
+// mode 2: new env object, same agent
 __global__ void rlm_init_kernel(DevPtrs ptr, int mode) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.n_envs) return;
   EnvHdr* e = (EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
   double* ring = (double*)((unsigned char*)e + sizeof(EnvHdr));
-  if (mode == 0) {
+  if (mode == 0 || mode == 2) {
+    // mode 2: a NEW env object for the SAME agent (`environment::Intraday<> env(c)` of main.cpp:219): the agent block
+    // (generator positions, rho, trace count, occupancy count) survives, everything else starts from scratch
+    AgentD keep;
+    if (mode == 2) keep = e->ag;
     unsigned char* raw = (unsigned char*)e;
     for (int i = 0; i < P.env_stride; ++i) raw[i] = 0;
     for (int i = 0; i < P.ring_total; ++i) ring[i] = 0.0;
     e->tp_val = -1.0;  // TargetPrice::val_ (target_price.cpp:8-10)
+    if (mode == 2) e->ag = keep;
   }
   side_reset(e->side[0]);
   side_reset(e->side[1]);
@@ -136,12 +142,15 @@ __global__ void rlm_gather_kernel(DevPtrs ptr, int what, void* out) {
 
 // ---------------------------------------------------------------------------------------------
 // parity record (include/rlm_record.h); lane 0 fills everything but the trace hash
-__device__ __noinline__ void fill_record(rlm_step_record* r, const EnvHdr& e, const AgentD& ag, unsigned long long thash) {
+// `vars`: the state written to the record (to-state of a learner step; decision state of a backtest step)
+__device__ __noinline__ void fill_record(rlm_step_record* r, const EnvHdr& e, const AgentD& ag, unsigned long long thash,
+                                         const float* vars) {
   r->step = ag.ep_step; r->action = ag.cur_action; r->time_ms = e.time_ms; r->terminal = is_terminal(e) ? 1 : 0;
   r->position = e.position; r->ask_quote = e.ask_quote; r->bid_quote = e.bid_quote;
   r->ask_level = e.ask_level; r->bid_level = e.bid_level;
   r->reward = ag.last_reward; r->pnl_step = e.pnl_step;
   r->ep_pnl = e.ep_pnl; r->ep_reward = e.ep_reward; r->ep_bandh = e.ep_bandh;
+  r->midprice = m_midprice(e); r->spread = m_spread(e); r->bandh_step = e.agg_mpm;  // LogProfit, intraday.cpp:437-451
   for (int s = 0; s < 2; ++s) {
     rlm_order_rec& o = s == 0 ? r->ask : r->bid;
     const OrderD& d = e.side[s].ord;
@@ -153,7 +162,7 @@ __device__ __noinline__ void fill_record(rlm_step_record* r, const EnvHdr& e, co
   r->market_buys = e.market_buys; r->market_sells = e.market_sells;
   r->lo_vol_step = e.lo_vol_step;
   r->n_state = P.n_state_vars;
-  for (int i = 0; i < RLM_N_STATE_MAX + 1; ++i) r->state[i] = (i < P.n_state_vars) ? ag.to_vars[i] : 0.0f;
+  for (int i = 0; i < RLM_N_STATE_MAX + 1; ++i) r->state[i] = (i < P.n_state_vars) ? vars[i] : 0.0f;
   r->delta = ag.last_delta;
   r->n_traces = ag.n_traces; r->pad = 0;
   r->trace_hash = thash;
@@ -195,7 +204,7 @@ __device__ __noinline__ void flow_next_warp(rlm_flow_state* s, rlm_tick_msg* m, 
 
 // One market tick of one env (thread-per-env).  Returns -1, or the ready kind: 0 = a learner step
 // ended (state variables + reward are in e.ag), 1 = warm-up ended (Intraday::Initialise done).
-__device__ __noinline__ int env_tick(EnvHdr& e, double* ring, const rlm_tick_msg& msg) {
+__device__ __noinline__ int env_tick(EnvHdr& e, double* ring, const rlm_tick_msg& msg, int backtest) {
   const int phase = e.phase;
   if (phase == PH_PREOPEN) {  // intraday.cpp:111-116: rows before the open only update the book
     rlm_tick_msg none = msg;
@@ -220,6 +229,10 @@ __device__ __noinline__ int env_tick(EnvHdr& e, double* ring, const rlm_tick_msg
     place_orders(e, 1, 1);
     e.phase = PH_RUN;
     e.ag.kind = 1;  // serial.cpp:24-25,55-60: the first from-state is the never-populated State
+    if (backtest) {  // Backtester::_step builds its state from the env before every action (serial.cpp:126)
+#pragma unroll 1
+      for (int i = 0; i < P.n_state_vars; ++i) e.ag.to_vars[i] = (float)get_variable(e, ring, P.state_vars[i]);
+    }
     return 1;
   }
   // tail of one iteration of performAction's do-while (base.cpp:292-305)
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
         }
         if (have) {
           const int was = e.phase;
-          ready = env_tick(e, ring, msg);
+          ready = env_tick(e, ring, msg, D.backtest);
           if (was != PH_PREOPEN) ticked = 1;
         }
       }
@@ -406,6 +419,9 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
         // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
         if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
         if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
+      } else if (ready == 1 && D.backtest) {
+        // Backtester::_step builds its state from the env before every action (serial.cpp:126), the first one included
+        if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
       }
     }
   }
@@ -421,6 +437,46 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
     const unsigned errs = (unsigned)(e.err | e.ag.err);
     if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
   }
+}
+
+// parity / profit-log record of one finished step (warp 0 of the CTA, or the env's warp)
+__device__ __noinline__ void emit_record(const DevPtrs& ptr, const EnvHdr* g, int env, const AgentD& ag, const double* theta_a,
+                                         const float* vars, int lane) {
+  const int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
+  const float* te = ptr.trace_e + (size_t)env * P.trace_cap;
+  unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
+  if (lane == 0) {
+    int c = ptr.record_count[env];
+    if (c < P.record_cap) {
+      EnvHdr tmp;
+      const int4* src = (const int4*)g;
+      int4* dst = (int4*)&tmp;
+      for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
+      fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h, vars);
+    }
+    ptr.record_count[env] = c + 1;
+  }
+}
+
+// Backtester::_step (serial.cpp:121-137) after a step ended (kind 0) or after Intraday::Initialise (kind 1):
+// the state of the NEXT action is the env's current one; nothing is learned.  q = Q_A/Q_B(state, .), lanes < A.
+__device__ __forceinline__ void backtest_advance(const DevPtrs& ptr, const EnvHdr* g, int env, AgentD& ag, const double* theta_a,
+                                                 int kind, double qa, double qb, unsigned long long base0, int lane,
+                                                 unsigned long long& steps_done) {
+  if (kind == 0) {
+    if (lane == 0) ag.last_delta = 0.0;
+    __syncwarp();
+    if (env < P.record_envs) emit_record(ptr, g, env, ag, theta_a, ag.from_vars, lane);  // state the action was chosen from
+    __syncwarp();
+  }
+  if (lane < P.n_actions) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
+  if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+  ag.from_base0[lane] = mod_m(base0);
+  if (lane == 0) {
+    ag.null_from = 0; ag.need_begin = 1;
+    if (kind == 0) { ag.n_steps++; ag.ep_step++; } else ag.kind = 2;
+  }
+  if (kind == 0) steps_done++;
 }
 
 // TD error + trace decision of Agent::HandleTransition (agent.cpp:86-101); lane 0.
@@ -552,7 +608,15 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   // once a quarter of an env's table is nonzero the bitmap test costs more than it saves: gather directly
   const unsigned* occ = (!P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size) ? nullptr : occ_w;
   unsigned long long bases[3];
-  if (stage == 2) {
+  if (D.backtest) {
+    const int kind = ag.kind;
+    if (kind == 0 || kind == 1) {
+      double qa, qb;
+      eval_q(s_rnd, theta_a, theta_b, ag.to_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc, occ);
+      __syncwarp();
+      backtest_advance(ptr, g, env, ag, theta_a, kind, qa, qb, bases[0], lane, steps_done);
+    }
+  } else if (stage == 2) {
     if (ag.kind == 0) {
       if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
       __syncwarp();
@@ -606,13 +670,13 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       if (lane == 0) {
         int c = ptr.record_count[env];
         if (c < P.record_cap) {
-          if (resident) fill_record(&ptr.records[(size_t)env * P.record_cap + c], *resident, ag, h);
+          if (resident) fill_record(&ptr.records[(size_t)env * P.record_cap + c], *resident, ag, h, ag.to_vars);
           else {
             EnvHdr tmp;
             const int4* src = (const int4*)g;
             int4* dst = (int4*)&tmp;
             for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
-            fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h);
+            fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h, ag.to_vars);
           }
         }
         ptr.record_count[env] = c + 1;
@@ -733,6 +797,25 @@ __device__ __noinline__ void a3_rho_step(AgentD& ag, const double* theta_a, cons
   __syncthreads();  // every warp has read from_vars
 }
 
+// Backtest mode (whole CTA), out of line like a3_rho_step
+__device__ __noinline__ int a3_backtest_step(const DevPtrs& ptr, const EnvHdr* g, int env, AgentD& ag, const double* theta_a,
+                                             const double* theta_b, const unsigned* occ, double* V, int kind, int warp, int lane) {
+  unsigned long long steps_done = 0;
+  int f[RLM_MAX_ACTIONS];
+  const unsigned long long base = a3_hash(rlm_rndseq_table, ag.to_vars, P.n_state_vars, false, warp, lane, f);
+  a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+  __syncthreads();
+  if (warp == 0) {
+    double qa = 0.0, qb = 0.0;
+    if (lane < P.n_actions) a3_sums(V, theta_b != nullptr, lane, qa, qb);
+    backtest_advance(ptr, g, env, ag, theta_a, kind, qa, qb, base, lane, steps_done);
+  }
+  return (int)steps_done;
+}
+
+// EXTRAS = false: the Q-learning / SARSA / Double-Q training kernel; EXTRAS = true adds the R-learning agents' third
+// evaluation and the backtest step (separate instantiation so that they cost the training path no registers).
+template <bool EXTRAS>
 __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -766,7 +849,9 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
     const int kind = ag.kind;
     int f[RLM_MAX_ACTIONS];
     unsigned long long base = 0ull;
-    if (stage == 2) {
+    if (EXTRAS && D.backtest) {
+      if (kind == 0 || kind == 1) steps_done += a3_backtest_step(ptr, g, env, ag, theta_a, theta_b, occ, V, kind, warp, lane);
+    } else if (stage == 2) {
       if (kind == 0) {  // shared policy, after theta += dtheta: Q(from = to-state, .) under theta_{t+1}
         base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);
         a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
@@ -817,22 +902,9 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
         __syncwarp();
         __threadfence();
-        if (env < P.record_envs) {
-          unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
-          if (lane == 0) {
-            int c = ptr.record_count[env];
-            if (c < P.record_cap) {
-              EnvHdr tmp;
-              const int4* src = (const int4*)g;
-              int4* dst = (int4*)&tmp;
-              for (int i = 0; i < (int)(sizeof(EnvHdr) / 16); ++i) dst[i] = __ldcg(src + i);
-              fill_record(&ptr.records[(size_t)env * P.record_cap + c], tmp, ag, h);
-            }
-            ptr.record_count[env] = c + 1;
-          }
-        }
+        if (env < P.record_envs) emit_record(ptr, g, env, ag, theta_a, ag.to_vars, lane);
       }
-      if (P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, V, q_pre_a, q_pre_b, dec, D, warp, lane);
+      if (EXTRAS && P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, V, q_pre_a, q_pre_b, dec, D, warp, lane);
       if (warp == 0 && stage == 0) {
         if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
         ag.from_base0[lane] = mod_m(base);
@@ -859,18 +931,21 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
   }
 }
 
-cudaError_t rlm_launch_agent3(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int tslot, int n_sms, int stage, cudaStream_t st) {
+cudaError_t rlm_launch_agent3(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int tslot, int n_sms, int stage, int full,
+                              cudaStream_t st) {
   const size_t smem = rlm_agent3_smem_bytes(is_double);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(rlm_agent3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t attr_smem[2] = {0, 0};
+  if (smem > attr_smem[full ? 1 : 0]) {
+    cudaError_t e = full ? cudaFuncSetAttribute(rlm_agent3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(rlm_agent3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_smem = smem;
+    attr_smem[full ? 1 : 0] = smem;
   }
   int grid = n_envs;            // worst case: every env is ready
   const int cap = n_sms * 16;   // then the grid-stride loop takes over
   if (grid > cap) grid = cap;
-  rlm_agent3_kernel<<<grid, A3_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
+  if (full) rlm_agent3_kernel<true><<<grid, A3_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
+  else rlm_agent3_kernel<false><<<grid, A3_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
   return cudaGetLastError();
 }
 
@@ -1149,7 +1224,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 4) rlm_run_kernel(DevPtrs ptr, Dy
       }
       if (have) {
         const int was = e.phase;
-        const int r = env_tick(e, ring, msg);
+        const int r = env_tick(e, ring, msg, 0);
         ticks_left--; tick_idx++;
         if (was != PH_PREOPEN) ticked++;
         if (r >= 0) {

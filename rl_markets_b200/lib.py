@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librlm.so")
 
 EXPORTS = [
-    "rlm_last_error", "rlm_abi_version", "rlm_config_default", "rlm_create", "rlm_destroy", "rlm_reset",
+    "rlm_last_error", "rlm_abi_version", "rlm_config_default", "rlm_create", "rlm_destroy", "rlm_reset", "rlm_set_mode", "rlm_new_env",
     "rlm_load_ticks", "rlm_run_ticks", "rlm_sync", "rlm_get_counters", "rlm_get_stats", "rlm_get_state",
     "rlm_get_reward", "rlm_get_actions", "rlm_get_rho", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
     "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_shared_tick_accumulate", "rlm_apply_dtheta",
@@ -48,6 +48,8 @@ def load():
     L.rlm_create.argtypes = [P(abi.Config), P(C.c_void_p)]
     L.rlm_destroy.argtypes = [C.c_void_p]
     L.rlm_reset.argtypes = [C.c_void_p]
+    L.rlm_set_mode.argtypes = [C.c_void_p, C.c_int32]
+    L.rlm_new_env.argtypes = [C.c_void_p, P(abi.FlowParams)]
     L.rlm_load_ticks.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.rlm_run_ticks.argtypes = [C.c_void_p, C.c_int32]
     L.rlm_sync.argtypes = [C.c_void_p]
@@ -118,6 +120,16 @@ class BatchedMarket:
 
     def reset(self):
         check(self.L.rlm_reset(self.h))
+
+    def set_mode(self, mode):
+        """abi.MODE_TRAIN (Learner::_step) or abi.MODE_BACKTEST (Backtester::_step, serial.cpp:121-137)."""
+        check(self.L.rlm_set_mode(self.h, mode))
+
+    def new_env(self, flow=None):
+        """Fresh env objects for the same agents (main.cpp:219); `flow` = synthetic-flow parameters of the new day."""
+        check(self.L.rlm_new_env(self.h, C.byref(flow) if flow is not None else None))
+        if flow is not None:
+            self.cfg.flow = flow
 
     def load_ticks(self, msgs, n_ticks):
         """msgs: ctypes array (or address) of TickMsg laid out [tick][env]; kept alive until sync()."""

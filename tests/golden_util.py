@@ -9,9 +9,19 @@ from rl_markets_b200 import abi, config
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def manifest():
+def _all_cases():
     with open(os.path.join(GOLD, "manifest.json")) as f:
         return json.load(f)
+
+
+def manifest():
+    """Single-episode training cases."""
+    return [c for c in _all_cases() if not c.get("backtest")]
+
+
+def backtest_manifest():
+    """Train-until-the-close, then evaluate (main.cpp:216-241) cases."""
+    return [c for c in _all_cases() if c.get("backtest")]
 
 
 def units():

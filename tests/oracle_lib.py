@@ -67,6 +67,8 @@ def lib():
         L.lobo_handle_terminal.argtypes = [C.c_void_p, C.c_int]
         L.lobo_go_greedy.argtypes = [C.c_void_p]
         L.lobo_reset.argtypes = [C.c_void_p]
+        L.lobo_set_backtest.argtypes = [C.c_void_p, C.c_int]
+        L.lobo_new_env.argtypes = [C.c_void_p]
         L.lobo_rho.argtypes = [C.c_void_p]
         L.lobo_rho.restype = C.c_double
         L.lobo_run_batch.restype = C.c_int64
@@ -106,7 +108,7 @@ def generate_ticks(cfg, env_index, n_ticks):
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "t.bin")
         subprocess.check_call([FLOW_CSV, "--seed", str(cfg.flow.seed), "--env", str(env_index), "--ticks",
-                               str(n_ticks), "--dt-ms", str(cfg.flow.dt_ms), "--packed", p])
+                               str(n_ticks), "--dt-ms", str(cfg.flow.dt_ms), "--t0-ms", str(cfg.flow.t0_ms), "--packed", p])
         raw = open(p, "rb").read()
     arr = (abi.TickMsg * n_ticks).from_buffer_copy(raw)
     return arr
@@ -157,13 +159,17 @@ def write_ref_yaml(path, ydict):
         f.write("\n".join(out) + "\n")
 
 
-def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=None, want_theta=False):
-    """Run the UNMODIFIED reference (oracle/_ref/ref_driver) on the CSV rendering of the same flow."""
+def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=None, want_theta=False, t0_ms=None,
+            test=None):
+    """Run the UNMODIFIED reference (oracle/_ref/ref_driver) on the CSV rendering of the same flow.
+    test = dict(flow_seed, env, ticks, t0_ms): also run main.cpp's evaluation phase (greedy agent, new env,
+    Backtester) on a second stream; its records come back as "test_records"."""
     assert have_ref(), "oracle/_ref/ref_driver not built"
     with tempfile.TemporaryDirectory() as d:
         md, tas = os.path.join(d, "x_md_1.csv"), os.path.join(d, "x_tas_1.csv")
+        t0 = [] if t0_ms is None else ["--t0-ms", str(t0_ms)]
         subprocess.check_call([FLOW_CSV, "--seed", str(flow_seed), "--env", str(env_index), "--ticks", str(n_ticks),
-                               "--dt-ms", str(dt_ms), "--md", md, "--tas", tas])
+                               "--dt-ms", str(dt_ms), "--md", md, "--tas", tas] + t0)
         cfgp = os.path.join(d, "cfg.yaml")
         write_ref_yaml(cfgp, ydict)
         dump = os.path.join(d, "steps.bin")
@@ -174,6 +180,13 @@ def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=
             cmd += ["--algo", algo]
         if want_theta:
             cmd += ["--theta", thp]
+        dump2 = os.path.join(d, "test_steps.bin")
+        if test:
+            md2, tas2 = os.path.join(d, "y_md_1.csv"), os.path.join(d, "y_tas_1.csv")
+            t02 = [] if test.get("t0_ms") is None else ["--t0-ms", str(test["t0_ms"])]
+            subprocess.check_call([FLOW_CSV, "--seed", str(test["flow_seed"]), "--env", str(test["env"]), "--ticks",
+                                   str(test["ticks"]), "--dt-ms", str(dt_ms), "--md", md2, "--tas", tas2] + t02)
+            cmd += ["--test-md", md2, "--test-tas", tas2, "--dump-test", dump2]
         out = subprocess.check_output(cmd)
         summary = json.loads(out.decode().strip().splitlines()[-1])
         raw = open(dump, "rb").read()
@@ -187,4 +200,11 @@ def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=
             for i in range(0, len(tr), 16):
                 idx, val = struct.unpack("<qd", tr[i:i + 16])
                 theta[idx] = val
-    return {"records": [recs[i] for i in range(n)], "summary": summary, "theta": theta, "_keep": recs}
+        test_records = None
+        if test:
+            raw2 = open(dump2, "rb").read()
+            n2 = len(raw2) // C.sizeof(abi.StepRecord)
+            recs2 = (abi.StepRecord * n2).from_buffer_copy(raw2)
+            test_records = [recs2[i] for i in range(n2)]
+    return {"records": [recs[i] for i in range(n)], "summary": summary, "theta": theta, "_keep": recs,
+            "test_records": test_records}

@@ -24,6 +24,45 @@ def test_golden_step_records_bitwise(oracle):
             assert not bad, "%s step %d: %r" % (case["name"], i, G.describe_diff(g, port["records"][i], bad))
 
 
+def test_golden_backtest_records_bitwise(oracle):
+    """Train until the close, then main.cpp:216-241 (GoGreedy, a new Intraday, Backtester) -- vs the reference."""
+    L = oracle.lib()
+    for case in G.backtest_manifest():
+        cfg = G.case_config(case)
+        cfg.flow.t0_ms = case["t0_ms"]
+        h = L.lobo_create(C.byref(cfg), case["env"])
+        ticks = oracle.lib_generate(cfg, case["env"], case["ticks"])
+        recs = (abi.StepRecord * case["ticks"])()
+        used = C.c_int64()
+        n1 = L.lobo_run(h, ticks, case["ticks"], -1, recs, case["ticks"], C.byref(used))
+        gold, _k = G.records(case["name"])
+        assert n1 == len(gold) > 100 and L.lobo_is_terminal(h) == 1
+        for i, g in enumerate(gold):
+            assert not abi.record_fields_equal(g, recs[i]), (case["name"], "train", i)
+        L.lobo_handle_terminal(h, 0)      # Learner::RunEpisode, serial.cpp:79
+        L.lobo_go_greedy(h)               # main.cpp:217
+        L.lobo_set_backtest(h, 1)
+        L.lobo_new_env(h)                 # main.cpp:219
+        t = case["test"]
+        cfg2 = config.from_dict(case["yaml"], flow_seed=t["flow_seed"])
+        cfg2.flow.t0_ms = t["t0_ms"]
+        ticks2 = oracle.lib_generate(cfg2, t["env"], t["ticks"])
+        recs2 = (abi.StepRecord * t["ticks"])()
+        n2 = L.lobo_run(h, ticks2, t["ticks"], -1, recs2, t["ticks"], C.byref(used))
+        gold2, _k2 = G.records(case["name"] + "_test")
+        assert n2 == len(gold2) > 100 and L.lobo_is_terminal(h) == 1
+        for i, g in enumerate(gold2):
+            bad = abi.record_fields_equal(g, recs2[i])
+            assert not bad, "%s evaluation step %d: %r" % (case["name"], i, G.describe_diff(g, recs2[i], bad))
+        st = abi.EnvStats()
+        L.lobo_stats(h, C.byref(st))
+        s = case["summary"]  # after Runner::RunEpisode's ClearInventory
+        assert (st.position, st.episode_pnl, st.episode_reward, st.ask_transactions, st.bid_transactions, st.market_buys,
+                st.market_sells) == (s["test_position"], s["test_ep_pnl"], s["test_ep_reward"], s["test_ask_tx"],
+                                     s["test_bid_tx"], s["test_market_buys"], s["test_market_sells"])
+        L.lobo_destroy(h)
+
+
 def test_order_vectors(oracle):
     """test/test_Order.cpp scenarios + seeded scripts, values produced by market::Order itself."""
     L = oracle.lib()

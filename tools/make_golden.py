@@ -40,6 +40,21 @@ CASES = [
 ]
 
 
+# train on one (short) synthetic day until the close, then main.cpp's evaluation phase (GoGreedy, a NEW Intraday,
+# Backtester::RunEpisode) on another one: steps_<name>.bin = training records, steps_<name>_test.bin = evaluation
+BACKTEST_CASES = [
+    dict(name="bt_q_learn_m8192", algo="q_learn", M=8192, flow_seed=21, env=4, ticks=1200, train_open_ticks=900,
+         test=dict(flow_seed=22, env=4, ticks=1000, open_ticks=700), over={"policy.eps_T": 3}),
+    dict(name="bt_double_q_m8192", algo="double_q_learn", M=8192, flow_seed=23, env=5, ticks=1200, train_open_ticks=900,
+         test=dict(flow_seed=24, env=5, ticks=1000, open_ticks=700), over={"learning.alpha_start": 0.01}),
+]
+
+
+def day_t0(cfg, open_ticks, dt_ms=250):
+    """t0 such that the market closes (venue close - 30 min, market.cpp:67-70) `open_ticks` rows after the first one."""
+    return int(cfg.close_ms) - 30 * 60000 - open_ticks * dt_ms
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     units = subprocess.check_output([ol.REF_UNITS]).decode()
@@ -61,6 +76,23 @@ def main():
                 f.write(bytes(r))
         manifest.append(dict(c, yaml=y, n_records=len(recs), summary=ref["summary"]))
         print(c["name"], len(recs), "records;", ref["summary"]["steps"], "reference steps")
+    for c in BACKTEST_CASES:
+        y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
+        seed = y["debug"]["random_seed"] + c["env"]
+        y_run = json.loads(json.dumps(y))
+        y_run["debug"]["random_seed"] = seed
+        cfg = config.from_dict(y)
+        t0 = day_t0(cfg, c["train_open_ticks"])
+        test = dict(c["test"], t0_ms=day_t0(cfg, c["test"]["open_ticks"]))
+        ref = ol.run_ref(y_run, c["flow_seed"], c["env"], c["ticks"], t0_ms=t0, test=test)
+        assert ref["summary"]["terminal"] == 1
+        for suffix, recs in (("", ref["records"]), ("_test", ref["test_records"])):
+            with open(os.path.join(GOLD, "steps_%s%s.bin" % (c["name"], suffix)), "wb") as f:
+                for r in recs:
+                    f.write(bytes(r))
+        manifest.append(dict(c, yaml=y, backtest=True, t0_ms=t0, test=test, n_records=len(ref["records"]),
+                             n_test_records=len(ref["test_records"]), summary=ref["summary"]))
+        print(c["name"], len(ref["records"]), "training records;", len(ref["test_records"]), "evaluation records")
     with open(os.path.join(GOLD, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)
 
