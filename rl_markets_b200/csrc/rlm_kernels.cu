@@ -439,8 +439,9 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   }
 }
 
-// parity / profit-log record of one finished step (warp 0 of the CTA, or the env's warp)
-__device__ __noinline__ void emit_record(const DevPtrs& ptr, const EnvHdr* g, int env, const AgentD& ag, const double* theta_a,
+// parity / profit-log record of one finished step (warp 0 of the CTA, or the env's warp).  Inlined into the training
+// kernel on purpose: as a call it costs the hot path ~200 bytes of register spills (ptxas call ABI).
+__device__ __forceinline__ void emit_record(const DevPtrs& ptr, const EnvHdr* g, int env, const AgentD& ag, const double* theta_a,
                                          const float* vars, int lane) {
   const int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
   const float* te = ptr.trace_e + (size_t)env * P.trace_cap;
@@ -458,6 +459,11 @@ __device__ __noinline__ void emit_record(const DevPtrs& ptr, const EnvHdr* g, in
   }
 }
 
+__device__ __noinline__ void emit_record_ool(const DevPtrs& ptr, const EnvHdr* g, int env, const AgentD& ag, const double* theta_a,
+                                             const float* vars, int lane) {
+  emit_record(ptr, g, env, ag, theta_a, vars, lane);
+}
+
 // Backtester::_step (serial.cpp:121-137) after a step ended (kind 0) or after Intraday::Initialise (kind 1):
 // the state of the NEXT action is the env's current one; nothing is learned.  q = Q_A/Q_B(state, .), lanes < A.
 __device__ __forceinline__ void backtest_advance(const DevPtrs& ptr, const EnvHdr* g, int env, AgentD& ag, const double* theta_a,
@@ -466,7 +472,7 @@ __device__ __forceinline__ void backtest_advance(const DevPtrs& ptr, const EnvHd
   if (kind == 0) {
     if (lane == 0) ag.last_delta = 0.0;
     __syncwarp();
-    if (env < P.record_envs) emit_record(ptr, g, env, ag, theta_a, ag.from_vars, lane);  // state the action was chosen from
+    if (env < P.record_envs) emit_record_ool(ptr, g, env, ag, theta_a, ag.from_vars, lane);  // state the action was chosen from
     __syncwarp();
   }
   if (lane < P.n_actions) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
@@ -903,13 +909,21 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         __syncwarp();
         __threadfence();
         if (env < P.record_envs) emit_record(ptr, g, env, ag, theta_a, ag.to_vars, lane);
+        if (!EXTRAS && stage == 0) {
+          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          ag.from_base0[lane] = mod_m(base);
+          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          steps_done++;
+        }
       }
-      if (EXTRAS && P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, V, q_pre_a, q_pre_b, dec, D, warp, lane);
-      if (warp == 0 && stage == 0) {
-        if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
-        ag.from_base0[lane] = mod_m(base);
-        if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
-        steps_done++;
+      if (EXTRAS) {
+        if (P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, V, q_pre_a, q_pre_b, dec, D, warp, lane);
+        if (warp == 0 && stage == 0) {  // (after the other warps have read from_vars in a3_rho_step)
+          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          ag.from_base0[lane] = mod_m(base);
+          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          steps_done++;
+        }
       }
       if (stage == 0) {  // Q(from = to-state, .) under the UPDATED theta (serial.cpp:55,60); indices are still in registers
         __syncthreads();
