@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RLM_ABI_VERSION 1
+#define RLM_ABI_VERSION 2
 
 typedef enum rlm_status {
   RLM_OK = 0,
@@ -71,7 +71,7 @@ enum { RLM_TP_YAML_MIDPRICE = 0, RLM_TP_YAML_MICROPRICE = 1, RLM_TP_YAML_VWAP = 
 enum { RLM_SOURCE_GENERATOR = 0, /* rlm_flow.h generator evaluated inside the tick kernel */
        RLM_SOURCE_STREAM = 1 };  /* rlm_tick_msg chunks uploaded with rlm_load_ticks      */
 
-#define RLM_MAX_BANDS 16
+#define RLM_MAX_BANDS 32 /* power of two (band search); the longest upstream table, NasdaqNordic / Oslo, has 17 bands */
 #define RLM_MAX_ACTIONS 9
 #define RLM_N_TILINGS 32
 

@@ -85,11 +85,14 @@ int main() {
 
   // ---------------------------------------------------------------- Market (test/test_Market.cpp)
   printf("\"market\": [\n");
-  const char* syms[2][2] = {{"AAL", "L"}, {"BAES", "L"}};
-  for (int si = 0; si < 2; ++si) {
+  const char* syms[][2] = {{"AAL", "L"}, {"BAES", "L"}, {"X", "AS"}, {"X", "BR"}, {"X", "CO"}, {"X", "DE"}, {"X", "HE"}, {"X", "I"},
+                           {"X", "MC"}, {"X", "MI"}, {"X", "OL"}, {"X", "PA"}, {"X", "S"}, {"X", "VX"}, {"X", "ST"}, {"X", "VI"}};
+  const int n_syms = (int)(sizeof(syms) / sizeof(syms[0]));
+  for (int si = 0; si < n_syms; ++si) {
     market::Market* m = market::Market::make_market(syms[si][0], syms[si][1]);
     vector<double> px = {2750.0, 2750.5, 702.1, 702.5, 1000.0, 999.9, 999.95, 4999.5, 5000.0, 5001.0, 0.5, 0.00005, 1.0, 12.345,
-                         49.99, 50.0, 99.999, 100.0, 123.45, 499.95, 500.0, 9999.0, 10000.0, 10002.5, 52500.0, 52501.0, 52487.0};
+                         49.99, 50.0, 99.999, 100.0, 123.45, 499.95, 500.0, 9999.0, 10000.0, 10002.5, 52500.0, 52501.0, 52487.0,
+                         20000.0, 45020.0, 85040.0, 123400.0};
     for (int i = 0; i < 60; ++i) px.push_back((lcg() % 6000000) / 1000.0 + 0.001 * (lcg() % 7));
     printf("  {\"symbol\": \"%s.%s\", \"px\": [", syms[si][0], syms[si][1]);
     for (size_t i = 0; i < px.size(); ++i) { printf("%s", i ? ", " : ""); p_d(px[i]); }
@@ -104,7 +107,7 @@ int main() {
     for (size_t i = 0; i < tq.size(); ++i) printf("%s%d", i ? ", " : "", tq[i]);
     printf("], \"price\": [");
     for (size_t i = 0; i < tq.size(); ++i) { printf("%s", i ? ", " : ""); p_d(m->ToPrice(tq[i])); }
-    printf("], \"open\": %ld, \"close\": %ld}%s\n", m->open_time(), m->close_time(), si == 0 ? "," : "");
+    printf("], \"open\": %ld, \"close\": %ld}%s\n", m->open_time(), m->close_time(), si + 1 < n_syms ? "," : "");
     delete m;
   }
   printf("],\n");

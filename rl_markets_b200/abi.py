@@ -9,7 +9,7 @@ import ctypes as C
 RLM_DEPTH = 5
 RLM_N_TX_MAX = 4
 RLM_N_STATE_MAX = 13
-RLM_MAX_BANDS = 16
+RLM_MAX_BANDS = 32
 RLM_MAX_ACTIONS = 9
 RLM_N_TILINGS = 32
 

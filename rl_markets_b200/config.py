@@ -9,8 +9,7 @@ included:
   * market.target_price.type is kept AS WRITTEN; the inverted selector of
     base.cpp:101-112 is applied inside the library (Appendix A1).
   * the fee key is upper-case TRANSACTION_FEE and unused (base.cpp:23, A12) -> ignored.
-  * venue tick tables: src/market/market.cpp:175-314 (LSE implemented; others are
-    SURVEY section 8f rank 4).
+  * venue tick tables and trading hours: src/market/market.cpp:40-61,142-314 (all 14 venues).
 """
 import ctypes as C
 
@@ -20,13 +19,37 @@ from . import abi
 
 HOUR, MINUTE = 3600000, 60000
 
-# src/market/market.cpp:206-245  LondonStockExchange
+# Tick-size tables of src/market/market.cpp:142-314, ascending (price from, tick size)
+_EURONEXT = [(0.0, 0.001), (10.0, 0.005), (50.0, 0.01), (100.0, 0.05)]                       # :142-149
+_NORDIC = [(0.0, 0.0001), (0.5, 0.0005), (1.0, 0.001), (2.0, 0.002), (5.0, 0.005), (10.0, 0.01), (50.0, 0.05),
+           (100.0, 0.1), (500.0, 0.5), (1000.0, 1.0), (5000.0, 5.0), (10000.0, 10.0), (20000.0, 20.0),
+           (40000.0, 40.0), (50000.0, 50.0), (80000.0, 80.0), (100000.0, 100.0)]             # :151-172, :263-283
 _LSE_A = [(0.0, 0.0001), (1.0, 0.0005), (5.0, 0.001), (10.0, 0.005), (50.0, 0.01), (100.0, 0.05),
-          (500.0, 0.1), (1000.0, 0.5), (5000.0, 1.0), (10000.0, 5.0)]
+          (500.0, 0.1), (1000.0, 0.5), (5000.0, 1.0), (10000.0, 5.0)]                        # :216-227
 _LSE_B = [(0.0, 0.0001), (0.5, 0.0005), (1.0, 0.001), (5.0, 0.005), (10.0, 0.01), (50.0, 0.05),
-          (100.0, 0.1), (500.0, 0.5), (1000.0, 1.0), (5000.0, 5.0), (10000.0, 10.0)]
+          (100.0, 0.1), (500.0, 0.5), (1000.0, 1.0), (5000.0, 5.0), (10000.0, 10.0)]         # :230-242, :294-306 (Swiss)
 _LSE_GROUP_A = {"AAL", "BATS", "GSK", "VOD", "HSBA"}
 _LSE_GROUP_B = {"BAES", "UU", "LGEN", "LSE", "NXT"}
+_MILAN = [(0.0, 0.0001), (0.25, 0.0005), (1.0, 0.001), (2.0, 0.0025), (5.0, 0.005), (50.0, 0.01)]  # :253-261
+_VIENNA = [(0.0, 0.001), (10.0, 0.005), (50.0, 0.01), (100.0, 0.5)]                          # :309-313 (0.5 is upstream's)
+
+# venue code -> (table, market open, market close); Market::make_market, market.cpp:40-61
+_VENUES = {
+    "AS": (_EURONEXT, 9 * HOUR, 17 * HOUR + 40 * MINUTE),   # Amsterdam :176-178
+    "BR": (_EURONEXT, 9 * HOUR, 17 * HOUR + 40 * MINUTE),   # Brussels :180-182
+    "CO": (_NORDIC, 9 * HOUR, 17 * HOUR),                   # Copenhagen :184-186
+    "DE": (_EURONEXT, 9 * HOUR, 17 * HOUR + 30 * MINUTE),   # Xetra :188-192 (same bands as Euronext)
+    "HE": (_NORDIC, 10 * HOUR, 16 * HOUR + 30 * MINUTE),    # Helsinki :194-196
+    "I": (_EURONEXT, 8 * HOUR, 16 * HOUR + 16 * MINUTE + 40),  # Irish :198-205: add_minutes(16, 40) = 16 min + 40 ms
+    "MC": (_EURONEXT, 9 * HOUR, 17 * HOUR + 30 * MINUTE),   # Madrid :247-251
+    "MI": (_MILAN, 9 * HOUR, 17 * HOUR + 25 * MINUTE),      # Milan :253-261
+    "OL": (_NORDIC, 9 * HOUR, 16 * HOUR + 30 * MINUTE),     # Oslo :263-283
+    "PA": (_EURONEXT, 9 * HOUR, 17 * HOUR + 30 * MINUTE),   # Paris :285-287
+    "S": (_LSE_B, 9 * HOUR, 17 * HOUR + 30 * MINUTE),       # Swiss :293-307
+    "VX": (_LSE_B, 9 * HOUR, 17 * HOUR + 30 * MINUTE),
+    "ST": (_NORDIC, 9 * HOUR, 17 * HOUR + 30 * MINUTE),     # Stockholm :289-291
+    "VI": (_VIENNA, 9 * HOUR, 17 * HOUR + 30 * MINUTE),     # Vienna :309-313
+}
 
 
 def venue_table(ticker):
@@ -41,7 +64,9 @@ def venue_table(ticker):
         else:
             raise ValueError('[LondonStockExchange] Unknown symbol "%s".' % symbol)
         return bands, 8 * HOUR, 16 * HOUR + 30 * MINUTE
-    raise ValueError('[Market] venue "%s" is not built yet (SURVEY.md 8f rank 4)' % venue)
+    if venue in _VENUES:
+        return _VENUES[venue]
+    raise ValueError('[Market] Unknown exchange venue "%s".' % venue)
 
 
 def _get(d, path, default=None, required=False):
@@ -164,7 +189,8 @@ def set_default_flow(c, seed, dt_ms):
     f.tick_hi = 57000 - 400
     f.band_tick0 = 49000
     f.dt_ms = dt_ms
-    f.t0_ms = 8 * HOUR + 30 * MINUTE
+    # first row right after the venue's open + 30 min guard (market.cpp:67-70); LSE: 08:30:00.000 as in rlm_flow.h
+    f.t0_ms = int(c.open_ms) + 30 * MINUTE if c.open_ms else 8 * HOUR + 30 * MINUTE
     f.date = 20100104
     f.vol0 = 500
     f.p_move_u12 = 1024

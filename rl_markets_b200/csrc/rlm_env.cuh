@@ -32,6 +32,7 @@ __device__ __forceinline__ long long d2ll_x86(double d) {
 }
 
 // ---------------------------------------------------------------- market::Market
+static_assert((RLM_MAX_BANDS & (RLM_MAX_BANDS - 1)) == 0, "the band search halves RLM_MAX_BANDS");
 // Market::ToTicks (market.cpp:78-102).  Bands below the one containing `price` contribute a
 // price-independent chain of truncating `int += double` steps, precomputed on the host
 // (VenueD::cum_full); the loop below is the reference loop entered at that band.

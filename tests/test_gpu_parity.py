@@ -50,6 +50,8 @@ _BOLTZ = {"policy.type": "boltzmann", "policy.tau_init": 0.1, "policy.tau_floor"
     ("r_learn", 16384, {"policy.eps_init": 0.3}), ("online_r_learn", 16384, {"policy.eps_init": 0.3}),
     ("double_r_learn", 8209, {"policy.eps_init": 0.3, "learning.alpha_start": 0.01}),
     ("q_learn", 8192, _BOLTZ), ("double_r_learn", 4096, dict(_BOLTZ, **{"learning.alpha_start": 0.01})),
+    # another venue's tick table and hours (NasdaqNordic, 17 bands, market.cpp:151-172,289-291)
+    ("sarsa", 8192, {"data.symbols": ["ERIC.ST"]}),
 ])
 def test_generator_mode_matches_oracle(rlm, oracle, algo, M, over):
     n_envs, n_ticks = 8, 3000
