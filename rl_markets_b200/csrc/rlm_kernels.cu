@@ -736,7 +736,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
 #define A3_DEC (A3_SS + 4 * SS_SLOTS)                      // 6 doubles
 #define A3_V (A3_DEC + 48)                                 // V[table][g][a][VROW]
 size_t rlm_agent3_smem_bytes(int is_double) {
-  return AG_BYTES + (((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 3 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
+  return AG_BYTES + (((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 4 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
 }
 
 // indices of lane j's tiles of group g for every action (registers), and the partial hash sum
@@ -751,6 +751,10 @@ __device__ __forceinline__ unsigned long long a3_hash(const unsigned* rnd, const
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a) f[a] = (a < A && !null_state) ? tile_index(rnd, base, nf, g * A + a) : 0;
   return base;
 }
+// V[table][seg][a][VROW] holds the PRODUCTS w*theta[f] of agent.cpp:117-135's four loops -- seg 0 = (group 0, w0),
+// 1 = (group 1, w1), 2 = (group 1, w2: the third loop starts at T, Appendix A8), 3 = (group 2, w2) -- so that the
+// multiplications are done by the gathering lanes, in parallel, and only the additions remain on the serial chain.
+#define A3_SEGS 4
 __device__ __forceinline__ void a3_gather(const double* th_a, const double* th_b, const unsigned* occ, const int* f, int g, int lane, double* V) {
   const int A = P.n_actions;
   double va[RLM_MAX_ACTIONS], vb[RLM_MAX_ACTIONS];
@@ -763,26 +767,52 @@ __device__ __forceinline__ void a3_gather(const double* th_a, const double* th_b
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) vb[a] = nz[a] ? __ldcg(th_b + f[a]) : 0.0;
   }
-  double* Va = V + (size_t)g * RLM_MAX_ACTIONS * VROW;
-  double* Vb = V + (size_t)(3 + g) * RLM_MAX_ACTIONS * VROW;
+  const int seg0 = (g == 0) ? 0 : ((g == 1) ? 1 : 3);
+  const double w = P.gw[g];
+  double* Va = V + (size_t)seg0 * RLM_MAX_ACTIONS * VROW;
+  double* Vb = V + (size_t)(A3_SEGS + seg0) * RLM_MAX_ACTIONS * VROW;
 #pragma unroll
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
     if (a < A) {
-      Va[a * VROW + lane] = va[a];
-      if (th_b) Vb[a * VROW + lane] = vb[a];
+      Va[a * VROW + lane] = w * va[a];
+      if (th_b) Vb[a * VROW + lane] = w * vb[a];
+    }
+  }
+  if (g == 1) {  // group 1 is summed a second time with w2
+    const double w2 = P.gw[2];
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+      if (a < A) {
+        Va[(RLM_MAX_ACTIONS + a) * VROW + lane] = w2 * va[a];
+        if (th_b) Vb[(RLM_MAX_ACTIONS + a) * VROW + lane] = w2 * vb[a];
+      }
     }
   }
 }
-// exact-order sums of agent.cpp:117-135 over the three gathered groups; lanes < A of warp 0
-__device__ __forceinline__ void a3_sums(const double* V, bool has_b, int lane, double& qa, double& qb) {
-  qa = 0.0; qb = 0.0;
+// Exact-order sum of agent.cpp:117-135 for one action: the 4 x 32 products of V's rows, strictly left to right.
+// Software-pipelined by hand -- block k+1 is loaded before block k is added, in a loop that is NOT unrolled: left to
+// itself ptxas pairs every shared-memory load with its addition (~37 cycles per element instead of ~10).
+__device__ __forceinline__ double a3_chain(const double* row0) {
+  double acc = 0.0, cur[8], nxt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cur[j] = row0[j];
 #pragma unroll 1
-  for (int seg = 0; seg < 4; ++seg) {  // (g0,w0) (g1,w1) (g1,w2) (g2,w2): the third loop starts at T (Appendix A8)
-    const int g = (seg == 0) ? 0 : ((seg == 3) ? 2 : 1);
-    const double w = P.gw[(seg == 0) ? 0 : ((seg == 1) ? 1 : 2)];
-    qa = seg_sum(qa, w, V + ((size_t)g * RLM_MAX_ACTIONS + lane) * VROW);
-    if (has_b) qb = seg_sum(qb, w, V + ((size_t)(3 + g) * RLM_MAX_ACTIONS + lane) * VROW);
+  for (int blk = 1; blk <= 4 * A3_SEGS; ++blk) {
+    const int nb = (blk < 4 * A3_SEGS) ? blk : 0;  // (the last iteration reloads block 0; its values are not used)
+    const double* r = row0 + (size_t)(nb >> 2) * RLM_MAX_ACTIONS * VROW + (nb & 3) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nxt[j] = r[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += cur[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
   }
+  return acc;
+}
+// exact-order sums over the four product rows; lanes < A of warp 0
+__device__ __noinline__ void a3_sums(const double* V, bool has_b, int lane, double& qa_out, double& qb_out) {
+  qa_out = a3_chain(V + (size_t)lane * VROW);
+  qb_out = has_b ? a3_chain(V + ((size_t)A3_SEGS * RLM_MAX_ACTIONS + lane) * VROW) : 0.0;
 }
 
 // R-learning agents (whole CTA): maxQ(from_state) under the UPDATED theta, then the rho update (td_rho).
@@ -819,6 +849,20 @@ __device__ __noinline__ int a3_backtest_step(const DevPtrs& ptr, const EnvHdr* g
   return (int)steps_done;
 }
 
+#ifdef RLM_TIMING  // debug build only (make EXTRA=-DRLM_TIMING): per-CTA phase timeline of the learner kernel
+__device__ long long g_phase_clk[4096 * 16];
+__device__ unsigned g_phase_sm[4096];
+#define PH(i) do { if (tid == 0 && idx < 4096) { g_phase_clk[idx * 16 + (i)] = clock64(); if ((i) == 0) { unsigned s_; asm volatile("mov.u32 %0, %%smid;" : "=r"(s_)); g_phase_sm[idx] = s_; } } } while (0)
+extern "C" int rlm_debug_read_phases(long long* clk, unsigned* sm) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(clk, g_phase_clk, sizeof(long long) * 4096 * 16) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(sm, g_phase_sm, sizeof(unsigned) * 4096) != cudaSuccess) return -1;
+  return 0;
+}
+#else
+#define PH(i) do { } while (0)
+#endif
+
 // EXTRAS = false: the Q-learning / SARSA / Double-Q training kernel; EXTRAS = true adds the R-learning agents' third
 // evaluation and the backtest step (separate instantiation so that they cost the training path no registers).
 template <bool EXTRAS>
@@ -838,6 +882,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
   unsigned long long steps_done = 0, sum_z = 0;
 #pragma unroll 1
   for (int idx = blockIdx.x; idx < n_ready; idx += gridDim.x) {
+    PH(0);
     const int env = ptr.ready[idx];
     EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
     __syncthreads();  // previous env's shared state is dead
@@ -847,6 +892,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       for (int i = tid; i < (int)(AG_BYTES / 16); i += A3_WARPS * 32) dst[i] = __ldcg(src + i);
     }
     __syncthreads();
+    PH(1);
     const size_t pol = P.shared_policy ? 0 : (size_t)env;
     double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
     double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
@@ -889,16 +935,21 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         __syncthreads();
       }
       base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);  // Q(to, .) under the current theta
+      PH(2);
       a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+      PH(3);
       __syncthreads();
+      PH(4);
       if (warp == 0) {
         int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
         float* te = ptr.trace_e + (size_t)env * P.trace_cap;
         if (lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
         __syncwarp();
+        PH(5);
         if (lane == 0)
           td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr, D, dec);
         __syncwarp();
+        PH(6);
         const float rate = (float)dec[0];
         const double scaled = dec[1];
         double* th = (dec[2] != 0.0) ? theta_b : theta_a;
@@ -907,7 +958,9 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
         sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
         __syncwarp();
+        PH(7);
         __threadfence();
+        PH(8);
         if (env < P.record_envs) emit_record(ptr, g, env, ag, theta_a, ag.to_vars, lane);
         if (!EXTRAS && stage == 0) {
           if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
@@ -927,17 +980,21 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       }
       if (stage == 0) {  // Q(from = to-state, .) under the UPDATED theta (serial.cpp:55,60); indices are still in registers
         __syncthreads();
+        PH(9);
         a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
         __syncthreads();
+        PH(10);
         if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       }
     }
     __syncthreads();
+    PH(11);
     {
       int4* dst = (int4*)&g->ag;
       const int4* src = (const int4*)&ag;
       for (int i = tid; i < (int)(AG_BYTES / 16); i += A3_WARPS * 32) __stcg(dst + i, src[i]);
     }
+    PH(12);
   }
   if (tid == 0 && (steps_done | sum_z)) {
     atomicAdd(&ptr.counters[1], steps_done);
