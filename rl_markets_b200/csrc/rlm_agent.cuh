@@ -162,6 +162,8 @@ struct QGather { double a[RLM_MAX_ACTIONS]; double b[RLM_MAX_ACTIONS]; };
 // policy, 32 MB for 4096 x 2^16) stays L2-resident, whereas theta (2 GB) does not: the test turns most
 // of a step's 864 random DRAM sector reads -- the measured limiter of the agent kernel -- into L2 hits.
 __device__ __forceinline__ bool occ_test(const unsigned* occ, int f) { return (__ldcg(occ + (f >> 5)) >> (f & 31)) & 1u; }
+// the same test on a copy of the bitmap staged in shared memory (rlm_agent3_kernel, small memory_size)
+__device__ __forceinline__ bool occ_test_s(const unsigned* occ_s, int f) { return (occ_s[f >> 5] >> (f & 31)) & 1u; }
 
 // idx: this warp's [27][32] tile-index cache in shared memory (row g*9+a, column lane).  The first
 // evaluation of a step fills it, the second one (same state, updated theta) just reads it back.
@@ -237,8 +239,23 @@ __device__ __noinline__ void eval_q(const unsigned* rnd, const double* th_a, con
   qb_out = qb;
 }
 
+// Address-space promises for the out-of-line learner functions: their pointer parameters are generic, and without
+// these ptxas emits the generic forms (LD/ST with a window check, and for atomics a QSPC + shared/global CAS-spin
+// fallback whose success predicate makes every atomicAdd wait for its L2 round trip).
+#define ASSUME_SHARED(p) __builtin_assume(__isShared((const void*)(p)))
+#define ASSUME_GLOBAL(p) __builtin_assume(__isGlobal((const void*)(p)))
+// theta[f] += v as a reduction performed at L2 (one IEEE fp64 add, round-to-nearest: the same rounding as the
+// reference's load-add-store); nothing is returned, so the warp does not wait for it
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_b32(unsigned* p, unsigned v) {
+  asm volatile("red.global.or.b32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+
 // argmax with rand() tie-breaks over q[0..A) (agent.cpp:144-169); lane 0
 __device__ __noinline__ int argmax_ties(AgentD& e, const double* q) {
+  ASSUME_SHARED(&e); ASSUME_SHARED(q);  // only the learner kernels call this: agent block and Q arrays are in shared memory
   int index = 0, n_ties = 1;
   double cur = q[0];
   for (int a = 1; a < P.n_actions; a++) {
@@ -325,44 +342,115 @@ __device__ __forceinline__ int last_writer(const int* ss, int f, bool null_from,
   return la;
 }
 
-__device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, double* theta, unsigned* occ, int action, float rate,
-                                       double scaled_update, int lane) {
+// The 3-warp learner kernel answers the same question with ONE probe: its two idle warps insert all A*32 tiles
+// of the from-state into a 512-slot table  feature -> last action that lists it  (keys in tt[0..512), values in
+// tt[512..1024)) while warp 0 computes the TD error; the serial trace pass then costs one lookup per entry instead
+// of A membership tests (cold, serial code runs at ~25 cycles per instruction here: instruction count is time).
+#define TT_SLOTS 512
+__device__ __forceinline__ unsigned tt_hash(int f) { return ((unsigned)f * 2654435761u) >> 23; }  // 9 bits
+__device__ __forceinline__ void tt_insert(int* tt, int f, int a) {
+  unsigned slot = tt_hash(f);
+  while (true) {
+    int old = atomicCAS(&tt[slot], HS_EMPTY, f);
+    if (old == HS_EMPTY || old == f) { atomicMax(&tt[TT_SLOTS + slot], a); return; }
+    slot = (slot + 1) & (TT_SLOTS - 1);
+  }
+}
+__device__ __forceinline__ int tt_last_writer(const int* tt, int f) {
+  unsigned slot = tt_hash(f);
+  while (true) {
+    int k = tt[slot];
+    if (k == f) return tt[TT_SLOTS + slot];
+    if (k == HS_EMPTY) return -1;
+    slot = (slot + 1) & (TT_SLOTS - 1);
+  }
+}
+// lanes of the building warps: thread t of n_threads inserts tiles t, t + n_threads, ... of the A*32 (tile j, action a)
+__device__ __forceinline__ void tt_build(int* tt, const AgentD& e, int t, int n_threads) {
+  for (int i = t; i < 2 * TT_SLOTS; i += n_threads) tt[i] = (i < TT_SLOTS) ? HS_EMPTY : -1;
+}
+__device__ __forceinline__ void tt_fill(int* tt, const AgentD& e, int t, int n_threads) {
+  const int n = P.n_actions * 32;
+  for (int i = t; i < n; i += n_threads) {
+    const int a = i >> 5, j = i & 31;
+    int f = e.from_base0[j] + P.ra_m[a];
+    if (f >= (int)P.memory_size) f -= (int)P.memory_size;
+    tt_insert(tt, f, a);
+  }
+}
+
+// occ: the policy's bitmap in HBM; occ_s: its shared-memory copy for this step, or nullptr
+#ifdef RLM_TIMING
+__device__ long long g_tp_clk[8];
+#define TP(i) do { if (lane == 0) tp_[i] = clock64(); } while (0)
+#else
+#define TP(i) do { } while (0)
+#endif
+// tt: the prebuilt tile table (see above), or nullptr: build the 128-slot set of the b_j in `ss` here
+__device__ __noinline__ int trace_pass(AgentD& e, int* ss, const int* tt, int* tf, float* te, double* theta, unsigned* occ, unsigned* occ_s,
+                                       int action, float rate, double scaled_update, int lane) {
+#ifdef RLM_TIMING
+  long long tp_[5] = {0, 0, 0, 0, 0};
+#endif
+  TP(0);
+  ASSUME_SHARED(&e); ASSUME_SHARED(ss); ASSUME_GLOBAL(tf); ASSUME_GLOBAL(te); ASSUME_GLOBAL(theta); ASSUME_GLOBAL(occ);
+  if (occ_s) ASSUME_SHARED(occ_s);
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];
-  for (int i = lane; i < SS_SLOTS; i += 32) ss[i] = HS_EMPTY;
-  __syncwarp();
-  if (!null_from) {
-    unsigned slot = ss_hash(b0);
-    while (true) {
-      int old = atomicCAS(&ss[slot], HS_EMPTY, b0);
-      if (old == HS_EMPTY || old == b0) break;
-      slot = (slot + 1) & (SS_SLOTS - 1);
+  if (tt) {
+    ASSUME_SHARED(tt);
+  } else {
+    for (int i = lane; i < SS_SLOTS; i += 32) ss[i] = HS_EMPTY;
+    __syncwarp();
+    if (!null_from) {
+      unsigned slot = ss_hash(b0);
+      while (true) {
+        int old = atomicCAS(&ss[slot], HS_EMPTY, b0);
+        if (old == HS_EMPTY || old == b0) break;
+        slot = (slot + 1) & (SS_SLOTS - 1);
+      }
     }
+    __syncwarp();
   }
-  __syncwarp();
+  TP(1);
   const float tol = 0.01f;
   int w = 0;
   if (rate != 0.0f) {
     const int n = e.n_traces;
+    // TR_AHEAD rounds of 32 entries are loaded at once (one memory round trip per chunk instead of one per
+    // round); the list is compacted in place, and a chunk only ever writes below the entries it has read
+#define TR_AHEAD 4
 #pragma unroll 1
-    for (int base = 0; base < n; base += 32) {
-      int i = base + lane;
-      bool valid = i < n;
-      int f = valid ? __ldcg(tf + i) : 0;
-      float ev = valid ? __ldcg(te + i) : 0.0f;
-      ev *= rate;
-      bool keep = valid && !(ev < tol);
-      if (keep) keep = last_writer(ss, f, null_from) < 0;
-      unsigned mask = __ballot_sync(FULL, keep);
-      int pos = w + __popc(mask & ((1u << lane) - 1u));
-      if (keep) {
-        __stcg(tf + pos, f);
-        __stcg(te + pos, ev);
-        atomicAdd(theta + f, scaled_update * (double)ev);  // one fp64 add performed at L2: same rounding as load-add-store
+    for (int base = 0; base < n; base += 32 * TR_AHEAD) {
+      int fq[TR_AHEAD];
+      float eq[TR_AHEAD];
+#pragma unroll
+      for (int k = 0; k < TR_AHEAD; ++k) {
+        const int i = base + 32 * k + lane;
+        fq[k] = (i < n) ? __ldcg(tf + i) : 0;
+        eq[k] = (i < n) ? __ldcg(te + i) : 0.0f;
       }
-      w += __popc(mask);
+#pragma unroll
+      for (int k = 0; k < TR_AHEAD; ++k) {
+        if (base + 32 * k < n) {  // warp-uniform
+          const int i = base + 32 * k + lane;
+          const int f = fq[k];
+          const float ev = eq[k] * rate;
+          bool keep = (i < n) && !(ev < tol);
+          if (keep) keep = ((tt && !null_from) ? tt_last_writer(tt, f) : last_writer(ss, f, null_from)) < 0;
+          unsigned mask = __ballot_sync(FULL, keep);
+          int pos = w + __popc(mask & ((1u << lane) - 1u));
+          if (keep) {
+            __stcg(tf + pos, f);
+            __stcg(te + pos, ev);
+            red_add_f64(theta + f, scaled_update * (double)ev);
+          }
+          w += __popc(mask);
+        }
+      }
     }
   }
+  TP(2);
   // set(): the taken action's tiles that no later action cleared; one entry per distinct f
   {
     int f = 0;
@@ -371,7 +459,10 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
       if (f >= (int)P.memory_size) f -= (int)P.memory_size;
     }
     // f is a tile of `action` by construction: only later actions can still clear it
-    bool add = null_from ? (action == P.n_actions - 1) : (last_writer(ss, f, false, action + 1) < 0);
+    bool add;
+    if (null_from) add = (action == P.n_actions - 1);
+    else if (tt) add = (tt_last_writer(tt, f) == action);  // f is listed by `action`; a later action would own the slot
+    else add = (last_writer(ss, f, false, action + 1) < 0);
     unsigned same = __match_any_sync(FULL, f);
     add = add && ((__ffs(same) - 1) == lane);
     unsigned mask = __ballot_sync(FULL, add);
@@ -387,19 +478,33 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, int* tf, float* te, d
       __stcg(tf + pos, f);
       __stcg(te + pos, 1.0f);
       const unsigned bit = 1u << (f & 31);
-      fresh = !(atomicOr(occ + (f >> 5), bit) & bit);  // every list entry was appended here once: its bit is set
-      atomicAdd(theta + f, scaled_update * (double)1.0f);
+      // every list entry was appended here once: its bit is set
+      if (occ_s) {
+        fresh = !(atomicOr(occ_s + (f >> 5), bit) & bit);  // shared-memory copy answers; HBM gets a fire-and-forget OR
+        red_or_b32(occ + (f >> 5), bit);
+      } else {
+        fresh = !(atomicOr(occ + (f >> 5), bit) & bit);
+      }
+      red_add_f64(theta + f, scaled_update * (double)1.0f);
     }
     const int n_fresh = __popc(__ballot_sync(FULL, fresh));
     if (lane == 0) e.n_occ += n_fresh;
     w = total;
   }
   __syncwarp();
+  TP(3);
+#ifdef RLM_TIMING
+  if (lane == 0 && tp_[3] - tp_[0] > g_tp_clk[0]) {  // keep the slowest pass seen (racy, debug only)
+    g_tp_clk[0] = tp_[3] - tp_[0]; g_tp_clk[1] = tp_[1] - tp_[0]; g_tp_clk[2] = tp_[2] - tp_[1]; g_tp_clk[3] = tp_[3] - tp_[2];
+    g_tp_clk[4] = e.n_traces; g_tp_clk[5] = (rate != 0.0f);
+  }
+#endif
   return w;
 }
 
 // order-independent hash of {(f, e, theta[f])} for the parity record
 __device__ __noinline__ unsigned long long trace_hash(const int* tf, const float* te, const double* theta, int n, int lane) {
+  ASSUME_GLOBAL(tf); ASSUME_GLOBAL(te); ASSUME_GLOBAL(theta);
   unsigned long long h = 0;
   for (int i = lane; i < n; i += 32) {
     int f = __ldcg(tf + i);

@@ -143,6 +143,9 @@ static int derive(rlm_handle_s* h) {
     p.ra_m[a] = (int)((unsigned long long)rlm_rndseq_table[(a + 449 * 4) & 2047] % (unsigned long long)c.memory_size);
   p.scratch_bytes = (int)rlm_scratch_bytes(p.is_double);
   p.occ_words = (int)((c.memory_size + 31) / 32);
+  // independent policies with a bitmap of <= 16 KB (memory_size <= 2^17): the 3-warp learner kernel keeps the env's
+  // bitmap in shared memory for the step, so the 1728 bit tests never touch the global load path
+  p.occ_smem_words = (!c.shared_policy && (size_t)p.occ_words * 4 <= 16384 && (p.occ_words & 3) == 0) ? p.occ_words : 0;  // (16-byte copies)
   p.gl = (float)(c.gamma * c.lambda);  // Traces::decay(float rate) narrows gamma*lambda (A11)
   for (int i = 0; i < 3; ++i) p.gw[i] = c.group_weights[i];
   p.gamma = c.gamma;
@@ -213,7 +216,7 @@ static int derive(rlm_handle_s* h) {
 static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tslot, int stage) {
   if (h->agent_variant == 3) {
     const int full = (d.backtest || h->cfg.algorithm >= RLM_ALGO_R_LEARN) ? 1 : 0;
-    return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, tslot, h->n_sms, stage, full, h->stream);
+    return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, h->hp.occ_smem_words, tslot, h->n_sms, stage, full, h->stream);
   }
   return rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, tslot, h->n_sms, stage, h->stream);
 }

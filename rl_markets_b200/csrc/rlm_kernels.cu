@@ -22,6 +22,7 @@
 #include "rlm_flow_tables.h"
 #include "rlm_rndseq.h"
 #include "rlm_agent.cuh"
+#include <cstdio>
 #include "rlm_kernels.h"
 
 // ---- agent-role shared memory: per warp [AgentD][scratch]  (the 8 KB hashing table is read through L1)
@@ -490,6 +491,7 @@ __device__ __forceinline__ void backtest_advance(const DevPtrs& ptr, const EnvHd
 // R-learning agents also hand out[3] = Q(from, action) and out[4] = the bootstrap value to td_rho
 __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, const double* q_pre_b, unsigned long long* mt_pol,
                                          unsigned long long* mt_agt, const DynParams& D, double* out) {
+  ASSUME_SHARED(&ag); ASSUME_SHARED(q_pre_a); ASSUME_SHARED(q_pre_b); ASSUME_SHARED(out); ASSUME_GLOBAL(mt_pol);
   const int action = ag.cur_action;
   const double reward = ag.last_reward;
   const double F_term = P.gamma * 0.0 - 0.0;  // potentials are 0 (base.cpp:239-242)
@@ -665,7 +667,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
       double* th = (dec[2] != 0.0) ? theta_b : theta_a;
       if (stage == 1) th = (dec[2] != 0.0) ? ptr.dtheta + P.memory_size : ptr.dtheta;  // accumulate, apply after the all-reduce
       __syncwarp();
-      int nz = trace_pass(ag, sset, tf, te, th, occ_w, ag.cur_action, rate, scaled, lane);
+      int nz = trace_pass(ag, sset, nullptr, tf, te, th, occ_w, nullptr, ag.cur_action, rate, scaled, lane);
       if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
       sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
     }
@@ -735,8 +737,11 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
 #define A3_SS (A3_Q + 8 * 2 * RLM_MAX_ACTIONS)             // small set
 #define A3_DEC (A3_SS + 4 * SS_SLOTS)                      // 6 doubles
 #define A3_V (A3_DEC + 48)                                 // V[table][g][a][VROW]
-size_t rlm_agent3_smem_bytes(int is_double) {
-  return AG_BYTES + (((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 4 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15);
+__host__ __device__ inline size_t a3_occ_offset(int is_double) {  // bytes from `sb` to the staged bitmap
+  return ((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 4 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15;
+}
+size_t rlm_agent3_smem_bytes(int is_double, int occ_smem_words) {
+  return AG_BYTES + a3_occ_offset(is_double) + (((size_t)occ_smem_words * 4 + 15) & ~(size_t)15);
 }
 
 // indices of lane j's tiles of group g for every action (registers), and the partial hash sum
@@ -755,12 +760,19 @@ __device__ __forceinline__ unsigned long long a3_hash(const unsigned* rnd, const
 // 1 = (group 1, w1), 2 = (group 1, w2: the third loop starts at T, Appendix A8), 3 = (group 2, w2) -- so that the
 // multiplications are done by the gathering lanes, in parallel, and only the additions remain on the serial chain.
 #define A3_SEGS 4
-__device__ __forceinline__ void a3_gather(const double* th_a, const double* th_b, const unsigned* occ, const int* f, int g, int lane, double* V) {
+// occ: bitmap to test (nullptr = dense table: gather everything); occ_sm: it is the shared-memory copy
+__device__ __forceinline__ void a3_gather(const double* th_a, const double* th_b, const unsigned* occ, bool occ_sm, const int* f, int g, int lane,
+                                          double* V) {
   const int A = P.n_actions;
   double va[RLM_MAX_ACTIONS], vb[RLM_MAX_ACTIONS];
   bool nz[RLM_MAX_ACTIONS];
+  if (occ_sm) {
 #pragma unroll
-  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) nz[a] = (a < A) && (occ == nullptr || occ_test(occ, f[a]));  // occ == nullptr: dense table
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) nz[a] = (a < A) && occ_test_s(occ, f[a]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) nz[a] = (a < A) && (occ == nullptr || occ_test(occ, f[a]));
+  }
 #pragma unroll
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a) va[a] = nz[a] ? __ldcg(th_a + f[a]) : 0.0;
   if (th_b) {
@@ -817,13 +829,13 @@ __device__ __noinline__ void a3_sums(const double* V, bool has_b, int lane, doub
 
 // R-learning agents (whole CTA): maxQ(from_state) under the UPDATED theta, then the rho update (td_rho).
 // Kept out of line so that its index registers do not weigh on the Q-learning / SARSA path.
-__device__ __noinline__ void a3_rho_step(AgentD& ag, const double* theta_a, const double* theta_b, const unsigned* occ, double* V,
+__device__ __noinline__ void a3_rho_step(AgentD& ag, const double* theta_a, const double* theta_b, const unsigned* occ, bool occ_sm, double* V,
                                          double* q_post_a, double* q_post_b, const double* dec, const DynParams& D, int warp, int lane) {
   const int A = P.n_actions;
   __syncthreads();  // trace pass done, V free
   int f2[RLM_MAX_ACTIONS];
   a3_hash(rlm_rndseq_table, ag.from_vars, P.n_state_vars, ag.null_from != 0, warp, lane, f2);
-  a3_gather(theta_a, theta_b, occ, f2, warp, lane, V);
+  a3_gather(theta_a, theta_b, occ, occ_sm, f2, warp, lane, V);
   __syncthreads();
   if (warp == 0) {
     if (lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_post_a[lane] = qa; q_post_b[lane] = qb; }
@@ -835,11 +847,11 @@ __device__ __noinline__ void a3_rho_step(AgentD& ag, const double* theta_a, cons
 
 // Backtest mode (whole CTA), out of line like a3_rho_step
 __device__ __noinline__ int a3_backtest_step(const DevPtrs& ptr, const EnvHdr* g, int env, AgentD& ag, const double* theta_a,
-                                             const double* theta_b, const unsigned* occ, double* V, int kind, int warp, int lane) {
+                                             const double* theta_b, const unsigned* occ, bool occ_sm, double* V, int kind, int warp, int lane) {
   unsigned long long steps_done = 0;
   int f[RLM_MAX_ACTIONS];
   const unsigned long long base = a3_hash(rlm_rndseq_table, ag.to_vars, P.n_state_vars, false, warp, lane, f);
-  a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+  a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
   __syncthreads();
   if (warp == 0) {
     double qa = 0.0, qb = 0.0;
@@ -857,6 +869,10 @@ extern "C" int rlm_debug_read_phases(long long* clk, unsigned* sm) {
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(clk, g_phase_clk, sizeof(long long) * 4096 * 16) != cudaSuccess) return -1;
   if (cudaMemcpyFromSymbol(sm, g_phase_sm, sizeof(unsigned) * 4096) != cudaSuccess) return -1;
+  long long tp[8];
+  if (cudaMemcpyFromSymbol(tp, g_tp_clk, sizeof(tp)) == cudaSuccess)
+    printf("slowest trace_pass so far: %lld cycles = set build %lld + decay loop %lld + set() %lld; n=%lld decay=%lld\n", tp[0], tp[1], tp[2], tp[3],
+           tp[4], tp[5]);
   return 0;
 }
 #else
@@ -876,6 +892,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
   int* sset = (int*)(sb + A3_SS);
   double* dec = (double*)(sb + A3_DEC);
   double* V = (double*)(sb + A3_V);
+  unsigned* occ_s = (unsigned*)(sb + a3_occ_offset(P.is_double));
   const unsigned* rnd = rlm_rndseq_table;
   const int A = P.n_actions;
   const int n_ready = ptr.ready_count[tslot];
@@ -886,27 +903,42 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
     const int env = ptr.ready[idx];
     EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
     __syncthreads();  // previous env's shared state is dead
+    const size_t pol = P.shared_policy ? 0 : (size_t)env;
+    unsigned* occ_w = ptr.occ + pol * (size_t)P.occ_words;
     {
       const int4* src = (const int4*)&g->ag;
       int4* dst = (int4*)&ag;
       for (int i = tid; i < (int)(AG_BYTES / 16); i += A3_WARPS * 32) dst[i] = __ldcg(src + i);
+      // the env's whole occupancy bitmap (<= 16 KB, L2-resident) rides along: one coalesced copy per step instead of
+      // 1728 scattered 4-byte loads on the step's critical path
+      const int n4 = P.occ_smem_words >> 2;
+      const int4* osrc = (const int4*)occ_w;
+      int4* odst = (int4*)occ_s;
+#pragma unroll 1
+      for (int i0 = tid; i0 < n4; i0 += 4 * A3_WARPS * 32) {  // 4 loads in flight per thread
+        int4 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = i0 + k * A3_WARPS * 32; if (i < n4) t[k] = __ldcg(osrc + i); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = i0 + k * A3_WARPS * 32; if (i < n4) odst[i] = t[k]; }
+      }
     }
     __syncthreads();
     PH(1);
-    const size_t pol = P.shared_policy ? 0 : (size_t)env;
     double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
     double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
-    unsigned* occ_w = ptr.occ + pol * (size_t)P.occ_words;
-    const unsigned* occ = (!P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size) ? nullptr : occ_w;
+    const bool dense = !P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size;
+    const bool occ_sm = !dense && P.occ_smem_words > 0;
+    const unsigned* occ = dense ? nullptr : (occ_sm ? occ_s : occ_w);
     const int kind = ag.kind;
     int f[RLM_MAX_ACTIONS];
     unsigned long long base = 0ull;
     if (EXTRAS && D.backtest) {
-      if (kind == 0 || kind == 1) steps_done += a3_backtest_step(ptr, g, env, ag, theta_a, theta_b, occ, V, kind, warp, lane);
+      if (kind == 0 || kind == 1) steps_done += a3_backtest_step(ptr, g, env, ag, theta_a, theta_b, occ, occ_sm, V, kind, warp, lane);
     } else if (stage == 2) {
       if (kind == 0) {  // shared policy, after theta += dtheta: Q(from = to-state, .) under theta_{t+1}
         base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);
-        a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+        a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
         __syncthreads();
         if (warp == 0) {
           double qa, qb;
@@ -919,7 +951,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       }
     } else if (kind == 1) {  // end of warm-up: Q(null state, .)
       a3_hash(rnd, ag.from_vars, P.n_state_vars, true, warp, lane, f);
-      a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+      a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
       __syncthreads();
       if (warp == 0) {
         double qa, qb;
@@ -929,32 +961,42 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
     } else if (kind == 0) {
       if (stage == 1) {  // shared policy: Q(from, .) under theta_t (agent.cpp:274,285 read theta at update time)
         a3_hash(rnd, ag.from_vars, P.n_state_vars, ag.null_from != 0, warp, lane, f);
-        a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+        a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
         __syncthreads();
         if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
         __syncthreads();
       }
       base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);  // Q(to, .) under the current theta
       PH(2);
-      a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+      a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
       PH(3);
       __syncthreads();
       PH(4);
+      if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
+      int* tt = (int*)V;  // the product rows are dead from here to the re-gather: the tile table lives there
+      __syncthreads();    // (warp 0 has read them)
+      PH(5);
+      if (warp != 0) {
+        // the two idle warps list every tile of the from-state with its last writer while warp 0 computes the TD error
+        tt_build(tt, ag, tid - 32, (A3_WARPS - 1) * 32);
+        asm volatile("bar.sync 1, %0;" ::"n"((A3_WARPS - 1) * 32) : "memory");  // slots initialised before any insert
+        if (!ag.null_from) tt_fill(tt, ag, tid - 32, (A3_WARPS - 1) * 32);
+      } else if (lane == 0) {
+        td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr, D, dec);
+      }
+      __syncthreads();
       if (warp == 0) {
         int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
         float* te = ptr.trace_e + (size_t)env * P.trace_cap;
-        if (lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
-        __syncwarp();
-        PH(5);
-        if (lane == 0)
-          td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, ptr.mt_agt ? ptr.mt_agt + (size_t)env * 312 : nullptr, D, dec);
-        __syncwarp();
         PH(6);
         const float rate = (float)dec[0];
         const double scaled = dec[1];
         double* th = (dec[2] != 0.0) ? theta_b : theta_a;
         if (stage == 1) th = (dec[2] != 0.0) ? ptr.dtheta + P.memory_size : ptr.dtheta;
-        int nz = trace_pass(ag, sset, tf, te, th, occ_w, ag.cur_action, rate, scaled, lane);
+#ifdef RLM_TIMING
+        if (tid == 0 && idx < 4096) { g_phase_clk[idx * 16 + 13] = ag.n_traces; g_phase_clk[idx * 16 + 14] = (rate != 0.0f); }
+#endif
+        int nz = trace_pass(ag, sset, tt, tf, te, th, occ_w, occ_sm ? occ_s : nullptr, ag.cur_action, rate, scaled, lane);
         if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
         sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
         __syncwarp();
@@ -970,7 +1012,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         }
       }
       if (EXTRAS) {
-        if (P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, V, q_pre_a, q_pre_b, dec, D, warp, lane);
+        if (P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, occ_sm, V, q_pre_a, q_pre_b, dec, D, warp, lane);
         if (warp == 0 && stage == 0) {  // (after the other warps have read from_vars in a3_rho_step)
           if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
           ag.from_base0[lane] = mod_m(base);
@@ -981,7 +1023,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       if (stage == 0) {  // Q(from = to-state, .) under the UPDATED theta (serial.cpp:55,60); indices are still in registers
         __syncthreads();
         PH(9);
-        a3_gather(theta_a, theta_b, occ, f, warp, lane, V);
+        a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
         __syncthreads();
         PH(10);
         if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
@@ -1002,9 +1044,9 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
   }
 }
 
-cudaError_t rlm_launch_agent3(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int tslot, int n_sms, int stage, int full,
-                              cudaStream_t st) {
-  const size_t smem = rlm_agent3_smem_bytes(is_double);
+cudaError_t rlm_launch_agent3(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int occ_smem_words, int tslot, int n_sms,
+                              int stage, int full, cudaStream_t st) {
+  const size_t smem = rlm_agent3_smem_bytes(is_double, occ_smem_words);
   static size_t attr_smem[2] = {0, 0};
   if (smem > attr_smem[full ? 1 : 0]) {
     cudaError_t e = full ? cudaFuncSetAttribute(rlm_agent3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)

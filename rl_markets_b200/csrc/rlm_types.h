@@ -114,6 +114,7 @@ struct DevParams {
   int trace_cap, record_envs, record_cap;
   int scratch_bytes;    // per-warp shared-memory scratch (depends on is_double)
   int occ_words;        // 32-bit words of the occupancy bitmap per policy
+  int occ_smem_words;   // > 0: the learner kernel stages an env's whole bitmap in shared memory (small memory_size)
   long long env_index0;
   VenueD venue;
   rlm_flow_params flow;

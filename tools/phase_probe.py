@@ -23,3 +23,13 @@ print("CTAs", len(a), "launch span (cycles)", a[:, 12].max() - a[:, 0].min(), "m
 print("start skew: p50 %d p99 %d" % (np.percentile(a[:, 0] - t0, 50), np.percentile(a[:, 0] - t0, 99)))
 for i, n in enumerate(names):
     print("%-28s mean %8.0f  p90 %8.0f  max %8.0f" % (n, d[:, i].mean(), np.percentile(d[:, i], 90), d[:, i].max()))
+
+order = np.argsort(-d[:, 6])[:12]
+print("slowest trace passes: cycles, n_traces before, decayed(rate != 0)")
+for i in order:
+    print("  %7d  n=%4d  decay=%d   (td_decision %d, gather %d)" % (d[i, 6], a[i, 13], a[i, 14], d[i, 5], d[i, 2]))
+import collections
+for dec in (0, 1):
+    sel = a[:, 14] == dec
+    if sel.any():
+        print("decay=%d: %d CTAs, trace_pass mean %.0f, n mean %.1f" % (dec, sel.sum(), d[sel, 6].mean(), a[sel, 13].mean()))
