@@ -851,6 +851,7 @@ __device__ __noinline__ int a3_backtest_step(const DevPtrs& ptr, const EnvHdr* g
   unsigned long long steps_done = 0;
   int f[RLM_MAX_ACTIONS];
   const unsigned long long base = a3_hash(rlm_rndseq_table, ag.to_vars, P.n_state_vars, false, warp, lane, f);
+  if (P.occ_smem_words) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncthreads(); }  // staged bitmap has landed
   a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
   __syncthreads();
   if (warp == 0) {
@@ -911,22 +912,20 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       for (int i = tid; i < (int)(AG_BYTES / 16); i += A3_WARPS * 32) dst[i] = __ldcg(src + i);
       // the env's whole occupancy bitmap (<= 16 KB, L2-resident) rides along: one coalesced copy per step instead of
       // 1728 scattered 4-byte loads on the step's critical path
+      // LDGSTS (cp.async, L2-coherent .cg): no registers, and the copy is only waited for right before the first gather
       const int n4 = P.occ_smem_words >> 2;
       const int4* osrc = (const int4*)occ_w;
-      int4* odst = (int4*)occ_s;
-#pragma unroll 1
-      for (int i0 = tid; i0 < n4; i0 += 4 * A3_WARPS * 32) {  // 4 loads in flight per thread
-        int4 t[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const int i = i0 + k * A3_WARPS * 32; if (i < n4) t[k] = __ldcg(osrc + i); }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const int i = i0 + k * A3_WARPS * 32; if (i < n4) odst[i] = t[k]; }
-      }
+      const unsigned odst = (unsigned)__cvta_generic_to_shared(occ_s);
+      for (int i = tid; i < n4; i += A3_WARPS * 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(odst + 16u * (unsigned)i), "l"(osrc + i) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __syncthreads();
     PH(1);
     double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
     double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
+    // every path below hashes first and gathers second: A3_OCC_READY() sits between the two
+#define A3_OCC_READY() do { if (P.occ_smem_words) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncthreads(); } } while (0)
     const bool dense = !P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size;
     const bool occ_sm = !dense && P.occ_smem_words > 0;
     const unsigned* occ = dense ? nullptr : (occ_sm ? occ_s : occ_w);
@@ -938,6 +937,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
     } else if (stage == 2) {
       if (kind == 0) {  // shared policy, after theta += dtheta: Q(from = to-state, .) under theta_{t+1}
         base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);
+        A3_OCC_READY();
         a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
         __syncthreads();
         if (warp == 0) {
@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       }
     } else if (kind == 1) {  // end of warm-up: Q(null state, .)
       a3_hash(rnd, ag.from_vars, P.n_state_vars, true, warp, lane, f);
+      A3_OCC_READY();
       a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
       __syncthreads();
       if (warp == 0) {
@@ -961,12 +962,14 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
     } else if (kind == 0) {
       if (stage == 1) {  // shared policy: Q(from, .) under theta_t (agent.cpp:274,285 read theta at update time)
         a3_hash(rnd, ag.from_vars, P.n_state_vars, ag.null_from != 0, warp, lane, f);
+        A3_OCC_READY();
         a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
         __syncthreads();
         if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
         __syncthreads();
       }
       base = a3_hash(rnd, ag.to_vars, P.n_state_vars, false, warp, lane, f);  // Q(to, .) under the current theta
+      if (stage != 1) A3_OCC_READY();
       PH(2);
       a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
       PH(3);
@@ -1029,6 +1032,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // (paths that gathered nothing)
     __syncthreads();
     PH(11);
     {
