@@ -322,6 +322,7 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
     h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
     if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
+    if (const char* s = getenv("RLM_PDL")) rlm_set_pdl(atoi(s));  // programmatic dependent launch of the per-tick kernels (default off: slower when measured)
     if (const char* s = getenv("RLM_AGENT_VARIANT")) h->agent_variant = (atoi(s) == 1) ? 1 : 3;
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches

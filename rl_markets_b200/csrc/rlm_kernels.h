@@ -18,6 +18,7 @@ int rlm_run_max_resident_ctas(int scratch_bytes, int n_sms);
 cudaError_t rlm_launch_init(const DevPtrs& ptr, int n_envs, int mode, cudaStream_t st);
 cudaError_t rlm_launch_seed(const DevPtrs& ptr, int n_envs, unsigned seed, cudaStream_t st);
 cudaError_t rlm_launch_random_init(const DevPtrs& ptr, int n_policies, cudaStream_t st);
+void rlm_set_pdl(int on);
 cudaError_t rlm_launch_gather(const DevPtrs& ptr, int n_envs, int what, void* out, cudaStream_t st);
 cudaError_t rlm_launch_clear_traces(const DevPtrs& ptr, int n_envs, cudaStream_t st);
 cudaError_t rlm_launch_test_to_ticks(const double* px, int n, int* out);
