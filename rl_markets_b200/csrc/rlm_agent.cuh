@@ -270,6 +270,28 @@ __device__ __noinline__ int argmax_ties(AgentD& e, const double* q) {
   }
   return index;
 }
+// The same scan, unrolled over values held in registers: the learner's serial TD step runs at ~25 cycles per
+// instruction, so the loop-carried shared-memory loads and the call of the version above are worth removing.
+// rand() is still drawn exactly when the reference draws it (only on ties with the running maximum).
+__device__ __forceinline__ int argmax_ties_fast(AgentD& e, const double* q) {
+  double v[RLM_MAX_ACTIONS];
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) v[a] = (a < P.n_actions) ? q[a] : 0.0;
+  int index = 0, n_ties = 1;
+  double cur = v[0];
+#pragma unroll
+  for (int a = 1; a < RLM_MAX_ACTIONS; ++a) {
+    if (a < P.n_actions) {
+      const double val = v[a];
+      if (val > cur) { cur = val; index = a; }
+      else if (val == cur) {
+        n_ties++;
+        if (0 == crand_next(e) % n_ties) { cur = val; index = a; }
+      }
+    }
+  }
+  return index;
+}
 // Greedy::Sample (policy.cpp:37-55); lane 0
 __device__ __noinline__ int greedy_sample(AgentD& e, const double* qs) {
   int argmax = 0, n_ties = 1;

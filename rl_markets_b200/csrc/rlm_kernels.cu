@@ -522,30 +522,30 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
     double Q2 = q_pre_a[a2];
     delta = reward + F_term + P.gamma * Q2 - Q1;
   } else if (P.algorithm == RLM_ALGO_Q_LEARN) {  // QLearn :272-292
-    int amax = argmax_ties(ag, ag.q_from);
+    int amax = argmax_ties_fast(ag, ag.q_from);
     if (action != amax) rate = 0.0f;
     double Q = ag.q_from[action];
-    int am2 = argmax_ties(ag, q_pre_a);
+    int am2 = argmax_ties_fast(ag, q_pre_a);
     delta = reward + F_term + P.gamma * q_pre_a[am2] - Q;
   } else if (P.algorithm == RLM_ALGO_DOUBLE_Q_LEARN) {  // DoubleQLearn :319-353
-    int amax = argmax_ties(ag, ag.q_from);
+    int amax = argmax_ties_fast(ag, ag.q_from);
     if (action != amax) rate = 0.0f;
     if (mt_uniform_real(mt_agt, ag.mt_agt_idx) > 0.5) {
       double Qa = ag.q_from[action];
-      int am2 = argmax_ties(ag, q_pre_a);
+      int am2 = argmax_ties_fast(ag, q_pre_a);
       delta = reward + F_term + P.gamma * q_pre_b[am2] - Qa;
       table = 0;
     } else {
       double Qb = ag.qb_from[action];
-      int am2 = argmax_ties(ag, q_pre_b);
+      int am2 = argmax_ties_fast(ag, q_pre_b);
       delta = reward + F_term + P.gamma * q_pre_a[am2] - Qb;
       table = 1;
     }
   } else if (P.algorithm == RLM_ALGO_R_LEARN) {  // RLearn :364-380
-    int amax = argmax_ties(ag, ag.q_from);
+    int amax = argmax_ties_fast(ag, ag.q_from);
     if (action != amax) rate = 0.0f;
     double Q = ag.q_from[action];
-    double mQ = q_pre_a[argmax_ties(ag, q_pre_a)];
+    double mQ = q_pre_a[argmax_ties_fast(ag, q_pre_a)];
     delta = reward - ag.rho + mQ - Q;
     out[3] = Q; out[4] = mQ;
   } else if (P.algorithm == RLM_ALGO_ONLINE_R_LEARN) {  // Agent::UpdateTraces :111-115, OnlineRLearn :398-405
@@ -554,16 +554,16 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
     delta = reward - ag.rho + gQ - Q;
     out[3] = Q; out[4] = gQ;
   } else {  // DoubleRLearn :422-451
-    int amax = argmax_ties(ag, ag.q_from);
+    int amax = argmax_ties_fast(ag, ag.q_from);
     if (action != amax) rate = 0.0f;
     double Q, mQ;
     if (mt_uniform_real(mt_agt, ag.mt_agt_idx) > 0.5) {
       Q = ag.q_from[action];
-      mQ = q_pre_b[argmax_ties(ag, q_pre_a)];
+      mQ = q_pre_b[argmax_ties_fast(ag, q_pre_a)];
       table = 0;
     } else {
       Q = ag.qb_from[action];
-      mQ = q_pre_a[argmax_ties(ag, q_pre_b)];
+      mQ = q_pre_a[argmax_ties_fast(ag, q_pre_b)];
       table = 1;
     }
     delta = reward - ag.rho + mQ - Q;
@@ -571,7 +571,7 @@ __device__ __noinline__ void td_decision(AgentD& ag, const double* q_pre_a, cons
   }
   ag.last_delta = delta;
   out[0] = (double)rate;
-  out[1] = (D.alpha * delta) / (double)RLM_N_TILINGS;  // Agent::updateQ: update / N_TILINGS
+  out[1] = (D.alpha * delta) * (1.0 / (double)RLM_N_TILINGS);  // Agent::updateQ: update / N_TILINGS (32: the reciprocal is exact)
   out[2] = (double)table;
 }
 
