@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.03)
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
@@ -182,8 +182,9 @@ def run_ours(args):
         m2 = lib.BatchedMarket(cfg2)
         m2.set_stream(stream.cuda_stream)
         n_warm = max(args.warmup, 3)
+        e2e_steps_n = min(args.steps, 20)  # 32 MB of pinned host memory per step at C1: the e2e leg times at most 20 of them
         nbytes = ticks * B * C.sizeof(abi.TickMsg)
-        gen_ticks = ticks * (n_warm + args.steps)
+        gen_ticks = ticks * (n_warm + e2e_steps_n)
         # synthetic messages for all envs, generated once on the host cores and staged in pinned host memory
         # BEFORE the timed region (one pinned chunk per bench step; nothing host-side is excluded from the timing)
         import numpy as np
@@ -203,23 +204,23 @@ def run_ours(args):
             m2.load_ticks(host.data_ptr(), ticks)
             m2.run_ticks(ticks)
             m2.sync()
-        chunks = [staged(n_warm + i) for i in range(args.steps)]
+        chunks = [staged(n_warm + i) for i in range(e2e_steps_n)]
         cc0 = m2.counters()
         barrier()
         t0 = time.perf_counter()
         # rlm_load_ticks double-buffers on a copy stream: the upload of step i+1 is issued before the result of
         # step i is read, so it overlaps step i's kernels; all K uploads and K read-backs are inside the region
         m2.load_ticks(chunks[0].data_ptr(), ticks)
-        for i in range(args.steps):
+        for i in range(e2e_steps_n):
             m2.run_ticks(ticks)
-            if i + 1 < args.steps:
+            if i + 1 < e2e_steps_n:
                 m2.load_ticks(chunks[i + 1].data_ptr(), ticks)   # H2D inside the timed region
             lib.check(m2.L.rlm_get_reward(m2.h, rew))  # D2H inside the timed region (syncs)
         barrier()
         wall = time.perf_counter() - t0
         cc1 = m2.counters()
         e2e_steps = cc1.steps - cc0.steps
-        e2e = {"steps": e2e_steps, "seconds": wall, "h2d": nbytes, "d2h": B * m2.cfg.n_state_vars * 0 + B * 8}
+        e2e = {"steps": e2e_steps, "seconds": wall, "h2d": nbytes, "d2h": B * 8, "n": e2e_steps_n}
         m2.close()
 
     # ---- aggregate over ranks: max time, sum steps
@@ -242,7 +243,7 @@ def run_ours(args):
         b_step = algorithmic_bytes_per_step(k_bar, z_bar, is_dq)
         value = steps_all / (total_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = rlm_agent_kernel (one launch per market tick); its algorithmic bytes are the agent
+        # dominant kernel = rlm_agent3_kernel (one launch per market tick); its algorithmic bytes are the agent
         # share of B_step: theta gathers + trace list (13824 + 28 Z per env step), SURVEY.md section 8d
         traffic = None
         try:
@@ -278,7 +279,8 @@ def run_ours(args):
             "gpu_launches": int(launches_timed),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "rlm_agent_kernel",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "rlm_agent3_kernel (learner step, one launch per market tick)",
                          "algorithmic_bytes_per_env_step_agent_kernel": b_agent,
                          "algorithmic_bytes_per_env_step_whole_path": b_step,
                          "whole_path_achieved_GBps": steps_all * b_step / (total_ms * 1e-3) / 1e9 / max(world, 1),
@@ -289,7 +291,8 @@ def run_ours(args):
         if e2e:
             line["e2e"] = {"value": e2e["steps"] / e2e["seconds"], "unit": "env_steps/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "note": "STREAM source: rlm_load_ticks from pinned host memory + rlm_run_ticks + rlm_get_reward per launch"}
+                           "steps": e2e["n"],
+                           "note": "STREAM source: rlm_load_ticks from pinned host memory (double-buffered upload) + rlm_run_ticks + rlm_get_reward per step"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_reference(args, n_procs=1, ticks=args.cpu_ticks)
         print(json.dumps(line))
@@ -327,24 +330,45 @@ def cpu_baseline_reference(args, n_procs, ticks):
                 "sample": "%d env(s) x %d ticks through oracle/liblob_oracle.so (in-memory ticks)" % (n_procs, ticks)}
     tmp = "/dev/shm" if os.path.isdir("/dev/shm") else None
     with tempfile.TemporaryDirectory(dir=tmp) as d:
-        cfgp = os.path.join(d, "cfg.yaml")
-        oracle_lib.write_ref_yaml(cfgp, y)
-        procs = []
-        for i in range(n_procs):
-            md, tas = os.path.join(d, "e%d_md_1.csv" % i), os.path.join(d, "e%d_tas_1.csv" % i)
-            subprocess.check_call([flow, "--seed", "2024", "--env", str(i), "--ticks", str(ticks), "--dt-ms", "1", "--md", md, "--tas", tas])
-        t0 = time.perf_counter()
-        for i in range(n_procs):
-            md, tas = os.path.join(d, "e%d_md_1.csv" % i), os.path.join(d, "e%d_tas_1.csv" % i)
-            procs.append(subprocess.Popen([drv, "--config", cfgp, "--md", md, "--tas", tas], stdout=subprocess.PIPE))
-        outs = [p.communicate()[0] for p in procs]
-        wall = time.perf_counter() - t0
-    steps = 0
-    inner = 0.0
+        cfgp = _ref_prepare(d, y, flow, n_procs, ticks)
+        res = _ref_run(d, cfgp, drv, n_procs)
+    return _ref_result(res, n_procs, ticks, algo)
+
+
+def _ref_prepare(d, y, flow, n_procs, ticks):
+    """Config + one synthetic CSV pair per process (written in parallel, on tmpfs, outside any timed region)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    cfgp = os.path.join(d, "cfg.yaml")
+    oracle_lib.write_ref_yaml(cfgp, y)
+    gens = []
+    for i in range(n_procs):
+        md, tas = os.path.join(d, "e%d_md_1.csv" % i), os.path.join(d, "e%d_tas_1.csv" % i)
+        gens.append(subprocess.Popen([flow, "--seed", "2024", "--env", str(i), "--ticks", str(ticks), "--dt-ms", "1", "--md", md, "--tas", tas]))
+    for g in gens:
+        if g.wait() != 0:
+            raise RuntimeError("flow_csv failed")
+    return cfgp
+
+
+def _ref_run(d, cfgp, drv, n_procs):
+    t0 = time.perf_counter()
+    procs = []
+    for i in range(n_procs):
+        md, tas = os.path.join(d, "e%d_md_1.csv" % i), os.path.join(d, "e%d_tas_1.csv" % i)
+        procs.append(subprocess.Popen([drv, "--config", cfgp, "--md", md, "--tas", tas], stdout=subprocess.PIPE))
+    outs = [p.communicate()[0] for p in procs]
+    wall = time.perf_counter() - t0
+    steps, inner = 0, 0.0
     for o in outs:
-        s = json.loads(o.decode().strip().splitlines()[-1])
-        steps += s["steps"]
-        inner = max(inner, s["seconds"])
+        r = json.loads(o.decode().strip().splitlines()[-1])
+        steps += r["steps"]
+        inner = max(inner, r["seconds"])
+    return steps, inner, wall
+
+
+def _ref_result(res, n_procs, ticks, algo):
+    steps, inner, wall = res
     return {"value": steps / inner, "unit": "env_steps/s", "cores": n_procs, "kind": "reference",
             "sample": "%d process(es) x %d synthetic ticks (%d learner steps), %s, CSV parsing included, "
                       "timed inside ref_driver (max over processes %.2fs; wall incl. process start %.2fs)"
@@ -356,12 +380,30 @@ def run_reference(args):
     if rank != 0:
         return
     n_procs = os.cpu_count() or 1
+    drv, flow = _ref_paths()
+    n_runs = max(args.warmup, 0) + args.steps
+    # one bench step = every host thread runs one single-env reference process over `ticks` ticks of the workload;
+    # the sample is sized so that the whole --steps/--warmup run stays within a few minutes (~1e5 ticks/s per process)
+    ticks = min(args.ref_ticks, max(10000, int(6e6 / max(n_runs, 1))))
     vals = []
     last = None
-    for i in range(max(args.warmup, 0) + args.steps):
-        last = cpu_baseline_reference(args, n_procs=n_procs, ticks=args.ref_ticks)
-        if i >= args.warmup:
-            vals.append(last)
+    if not os.path.exists(drv):
+        for i in range(n_runs):
+            last = cpu_baseline_reference(args, n_procs=n_procs, ticks=ticks)  # oracle port fallback
+            if i >= args.warmup:
+                vals.append(last)
+    else:
+        from rl_markets_b200 import config
+        w0 = WORKLOADS[args.workload]
+        algo = args.algo or w0["algo"]
+        y = config.example_dict(**{"learning.memory_size": args.memory_size or w0["memory_size"], "learning.algorithm": algo})
+        tmp = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        with tempfile.TemporaryDirectory(dir=tmp) as d:
+            cfgp = _ref_prepare(d, y, flow, n_procs, ticks)
+            for i in range(n_runs):
+                last = _ref_result(_ref_run(d, cfgp, drv, n_procs), n_procs, ticks, algo)
+                if i >= args.warmup:
+                    vals.append(last)
     value = sum(v["value"] for v in vals) / len(vals)
     w = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "env steps/sec (batched LOBs)", "value": value, "unit": "env_steps/s",
@@ -379,7 +421,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1", choices=sorted(WORKLOADS))

@@ -360,13 +360,21 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
   double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
   {
-    const int ph = g->phase, nb = g->ag.need_begin;  // uniform: skip idle envs without staging them
-    if (ph == PH_DONE || (only_begin && !nb)) return;
+    // the trailing begin-only pass touches few envs: look before staging.  A tick pass stages straight away -- one
+    // memory round trip instead of two on every env's critical path -- and drops finished envs afterwards.
+    if (only_begin && !g->ag.need_begin) return;
     const int4* src = (const int4*)g;
     int4* dst = (int4*)&e;
-    for (int i = lane; i < hdr_bytes / 16; i += 32) dst[i] = src[i];
+    const int n16 = hdr_bytes / 16;
+    static_assert(sizeof(EnvHdr) <= 4 * 32 * 16, "four 16-byte loads per lane cover the env header");
+    int4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < n16) t[k] = src[i]; }  // all in flight together
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < n16) dst[i] = t[k]; }
   }
   __syncwarp();
+  if (e.phase == PH_DONE) return;
   int ready = -1;
   unsigned ticked = 0;
   if (e.ag.need_begin) {
