@@ -132,6 +132,42 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- cold start (informational): the first steps of training from all-zero weight tables.  They are cheap -- the
+    # learner kernel skips gathers of weights that were never written -- and NOT representative of a training run,
+    # which keeps theta across ~1000 episodes (src/main.cpp:47-80): reported next to the headline, never as it.
+    cold = None
+    if args.pretrain_ticks > 0:
+        for _ in range(3):
+            run_chunk()
+        m.sync()
+        cc_a = m.counters()
+        n_cold = min(args.steps, 20)
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            ev_a.record(stream)
+            for _ in range(n_cold):
+                run_chunk()
+            ev_b.record(stream)
+        barrier()
+        m.sync()
+        cold = {"ms": ev_a.elapsed_time(ev_b), "steps": m.counters().steps - cc_a.steps, "n": n_cold}
+        # ---- pre-training (untimed): one reference trading day (LSE, 250 ms rows: 108 000 ticks) so that the timed
+        # region sees weight tables in their long-run state
+        left = args.pretrain_ticks
+        while left > 0:
+            if shared and world > 1:
+                with torch.cuda.stream(stream):
+                    parallel.run_shared_policy(m, min(left, 256), dist_mod)
+            else:
+                m.run_ticks(min(left, 256))
+            left -= 256
+        m.sync()
+    occ_start = None
+    if not shared:
+        o = m.occupancy()
+        occ_start = sum(o) / len(o) / float(args.memory_size or w["memory_size"])
+
     # ---- device-resident run (inputs = generator state, theta, traces: all in HBM)
     for _ in range(max(args.warmup, 3)):
         run_chunk()
@@ -152,6 +188,8 @@ def run_ours(args):
     c1 = m.counters()
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    if rank == 0 and os.environ.get("RLM_BENCH_TRACE"):  # how the step time moves as the weight tables fill up
+        sys.stderr.write("ms per bench step: " + " ".join("%.2f" % x for x in per_launch_ms[::max(1, args.steps // 40)]) + "\n")
     steps_done = c1.steps - c0.steps
     ticks_done = c1.ticks - c0.ticks
     z_sum = c1.sum_traces - c0.sum_traces
@@ -181,6 +219,7 @@ def run_ours(args):
         cfg2.device = local
         m2 = lib.BatchedMarket(cfg2)
         m2.set_stream(stream.cuda_stream)
+        m2.copy_theta_from(m)  # same long-run weight tables as the device-resident leg (a new data day, trained agent)
         n_warm = max(args.warmup, 3)
         e2e_steps_n = min(args.steps, 20)  # 32 MB of pinned host memory per step at C1: the e2e leg times at most 20 of them
         nbytes = ticks * B * C.sizeof(abi.TickMsg)
@@ -236,6 +275,14 @@ def run_ours(args):
     else:
         steps_all, ticks_all, z_all = float(steps_done), float(ticks_done), float(z_sum)
 
+    if cold is not None:
+        if world > 1:
+            import torch.distributed as dist
+            tc = torch.tensor([cold["ms"]], device="cuda", dtype=torch.float64)
+            sc = torch.tensor([float(cold["steps"])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+            cold["ms"], cold["steps"] = float(tc[0]), float(sc[0])
     if rank == 0:
         k_bar = ticks_all / max(steps_all, 1.0)
         z_bar = z_all / max(steps_all, 1.0)
@@ -275,7 +322,12 @@ def run_ours(args):
                        "policy": "shared theta, one SUM all-reduce of dtheta per tick" if shared else "independent theta per env, no collective",
                        "l2": ("working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * (args.memory_size or w["memory_size"]) * 8 / 1e9))
                              if not shared else ("shared theta %.0f MB (L2-resident) + %.1f GB of env records, traces and generator state" % ((args.memory_size or w["memory_size"]) * 8 / 1e6, B * 8.0e3 / 1e9)),
-                       "ticks_per_s": ticks_all / (total_ms * 1e-3)},
+                       "ticks_per_s": ticks_all / (total_ms * 1e-3),
+                       "pretrain_ticks": args.pretrain_ticks,
+                       "theta_occupancy_at_start": occ_start,
+                       "state": ("timed after %d ticks of training per env (one LSE trading day of the reference's 250 ms rows): "
+                                 "long-run weight tables" % args.pretrain_ticks) if args.pretrain_ticks > 0
+                                else "cold start: all-zero weight tables (gathers of never-written weights are skipped)"},
             "gpu_launches": int(launches_timed),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -288,6 +340,9 @@ def run_ours(args):
                          "env_kernel_avg_launch_ms": env_avg_ms,
                          "timing": "CUDA events around every kernel launch on the launching stream, separate pass"},
         }
+        if cold is not None:
+            line["cold_start"] = {"value": cold["steps"] / (cold["ms"] * 1e-3), "unit": "env_steps/s", "steps": cold["n"],
+                                  "note": "first bench steps of training from all-zero weight tables; informational, not the headline"}
         if e2e:
             line["e2e"] = {"value": e2e["steps"] / e2e["seconds"], "unit": "env_steps/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -421,7 +476,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1", choices=sorted(WORKLOADS))
@@ -429,6 +484,8 @@ def main():
     ap.add_argument("--algo", default="")
     ap.add_argument("--memory-size", dest="memory_size", type=int, default=0)
     ap.add_argument("--ticks", type=int, default=TICKS_PER_LAUNCH)
+    ap.add_argument("--pretrain-ticks", dest="pretrain_ticks", type=int, default=108000,
+                    help="untimed training before the timed region (default: one LSE day of 250 ms rows); 0 = cold start")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-distinct", type=int, default=64, help="distinct host-generated streams replayed across envs in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -190,6 +190,14 @@ int rlm_get_actions(rlm_handle h, int32_t* out /* [n_envs] last action */);
 /* rho of the R-learning agents (RLearn / OnlineRLearn / DoubleRLearn private member, include/rl/agent.h:131,145,157;
    the reference never prints it -- exposed here so that parity of the average-reward estimate can be checked) */
 int rlm_get_rho(rlm_handle h, double* out /* [n_envs] */);
+/* theta (both tables of a double agent) of every policy of `src` -> `dst`, device to device: the B-env form of handing one
+   trained `Agent*` to the next phase (src/main.cpp:196-222 keeps `m` across training episodes and into evaluation).  The
+   handles must agree in device, n_envs / shared_policy, memory_size and algorithm family; traces and env state of `dst`
+   are untouched. */
+int rlm_copy_theta(rlm_handle dst, rlm_handle src);
+/* Diagnostic (no reference counterpart): number of weights of env b's table A that have ever been written, i.e. the
+   population of the occupancy bitmap the learner kernel uses to skip gathers of exact zeros (independent policies). */
+int rlm_get_occupancy(rlm_handle h, int32_t* out /* [n_envs] */);
 
 int rlm_handle_terminal(rlm_handle h, int32_t episode);
 int rlm_go_greedy(rlm_handle h);

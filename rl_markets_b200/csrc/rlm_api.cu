@@ -612,6 +612,10 @@ int rlm_get_reward(rlm_handle h, double* out) {
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   return fetch_column(h, 0, out, (size_t)h->cfg.n_envs * sizeof(double));
 }
+int rlm_get_occupancy(rlm_handle h, int32_t* out) {
+  if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  return fetch_column(h, 4, out, (size_t)h->cfg.n_envs * sizeof(int32_t));
+}
 int rlm_get_rho(rlm_handle h, double* out) {
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   return fetch_column(h, 3, out, (size_t)h->cfg.n_envs * sizeof(double));
@@ -669,6 +673,25 @@ int rlm_write_theta(rlm_handle h, int32_t policy, int32_t table, const double* i
     const int dense = (int)h->cfg.memory_size;
     CK(cudaMemcpy(h->ptr.env + (size_t)policy * h->hp.env_stride + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), &dense, 4, cudaMemcpyHostToDevice));
   }
+  return RLM_OK;
+}
+
+int rlm_copy_theta(rlm_handle dst, rlm_handle src) {
+  if (!dst || !src) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  if (dst->cfg.device != src->cfg.device || dst->n_policies != src->n_policies || dst->cfg.memory_size != src->cfg.memory_size ||
+      dst->hp.is_double != src->hp.is_double || dst->cfg.shared_policy != src->cfg.shared_policy)
+    return fail(RLM_ERR_INVALID_ARGUMENT, "rlm_copy_theta: handles differ in device, policy count, memory_size or table count");
+  CK(cudaSetDevice(dst->cfg.device));
+  CK(cudaStreamSynchronize(src->stream));
+  CK(cudaStreamSynchronize(dst->stream));
+  const size_t tbytes = (size_t)src->n_policies * (size_t)src->cfg.memory_size * 8;
+  CK(cudaMemcpy(dst->ptr.theta, src->ptr.theta, tbytes, cudaMemcpyDeviceToDevice));
+  if (src->ptr.theta_b) CK(cudaMemcpy(dst->ptr.theta_b, src->ptr.theta_b, tbytes, cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(dst->ptr.occ, src->ptr.occ, (size_t)src->n_policies * (size_t)src->hp.occ_words * 4, cudaMemcpyDeviceToDevice));
+  if (!src->cfg.shared_policy)  // per-env population count of the bitmap (AgentD::n_occ) travels with it
+    CK(cudaMemcpy2D(dst->ptr.env + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), dst->hp.env_stride,
+                    src->ptr.env + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), src->hp.env_stride, 4, src->cfg.n_envs,
+                    cudaMemcpyDeviceToDevice));
   return RLM_OK;
 }
 

@@ -154,6 +154,7 @@ __global__ void rlm_gather_kernel(DevPtrs ptr, int what, void* out) {
   if (what == 0) ((double*)out)[b] = e->ag.last_reward;
   else if (what == 1) ((int*)out)[b] = e->last_action;
   else if (what == 3) ((double*)out)[b] = e->ag.rho;
+  else if (what == 4) ((int*)out)[b] = e->ag.n_occ;
   else
     for (int k = 0; k < P.n_state_vars; ++k) ((float*)out)[(size_t)b * P.n_state_vars + k] = e->ag.from_vars[k];
 }
@@ -953,7 +954,10 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
     double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
     // every path below hashes first and gathers second: A3_OCC_READY() sits between the two
 #define A3_OCC_READY() do { if (P.occ_smem_words) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncthreads(); } } while (0)
-    const bool dense = !P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size;
+    // the bitmap test pays for itself as long as it filters enough gathers: against HBM-resident bitmaps up to a
+    // quarter full, against the shared-memory copy (a test is one LDS) up to 15/16 full
+    const bool dense = !P.shared_policy && (P.occ_smem_words > 0 ? (long long)ag.n_occ * 16 > P.memory_size * 15
+                                                                  : (long long)ag.n_occ * 4 > P.memory_size);
     const bool occ_sm = !dense && P.occ_smem_words > 0;
     const unsigned* occ = dense ? nullptr : (occ_sm ? occ_s : occ_w);
     const int kind = ag.kind;

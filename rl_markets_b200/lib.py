@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "librlm.so")
 EXPORTS = [
     "rlm_last_error", "rlm_abi_version", "rlm_config_default", "rlm_create", "rlm_destroy", "rlm_reset", "rlm_set_mode", "rlm_new_env",
     "rlm_load_ticks", "rlm_run_ticks", "rlm_sync", "rlm_get_counters", "rlm_get_stats", "rlm_get_state",
-    "rlm_get_reward", "rlm_get_actions", "rlm_get_rho", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
+    "rlm_get_reward", "rlm_get_actions", "rlm_get_rho", "rlm_get_occupancy", "rlm_copy_theta", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
     "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_shared_tick_accumulate", "rlm_apply_dtheta",
     "rlm_set_stream", "rlm_set_profiling", "rlm_get_kernel_times",
     "rlm_flow_generate", "rlm_test_to_ticks", "rlm_test_to_price", "rlm_test_tiles", "rlm_test_order",
@@ -59,6 +59,8 @@ def load():
     L.rlm_get_reward.argtypes = [C.c_void_p, P(C.c_double)]
     L.rlm_get_actions.argtypes = [C.c_void_p, P(C.c_int32)]
     L.rlm_get_rho.argtypes = [C.c_void_p, P(C.c_double)]
+    L.rlm_get_occupancy.argtypes = [C.c_void_p, P(C.c_int32)]
+    L.rlm_copy_theta.argtypes = [C.c_void_p, C.c_void_p]
     L.rlm_handle_terminal.argtypes = [C.c_void_p, C.c_int32]
     L.rlm_go_greedy.argtypes = [C.c_void_p]
     L.rlm_read_theta.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(C.c_double), C.c_int64]
@@ -175,6 +177,16 @@ class BatchedMarket:
     def rho(self):
         out = (C.c_double * self.cfg.n_envs)()
         check(self.L.rlm_get_rho(self.h, out))
+        return out
+
+    def copy_theta_from(self, other):
+        """Take over the trained weights of another handle (same shape, same device)."""
+        check(self.L.rlm_copy_theta(self.h, other.h))
+
+    def occupancy(self):
+        """Written weights per env (population of the gather-skipping bitmap); diagnostic."""
+        out = (C.c_int32 * self.cfg.n_envs)()
+        check(self.L.rlm_get_occupancy(self.h, out))
         return out
 
     def handle_terminal(self, episode):
