@@ -401,6 +401,14 @@ __device__ __forceinline__ void tt_fill(int* tt, const AgentD& e, int t, int n_t
   }
 }
 
+// 4096-bit filter of the features whose weight this step's update touched (every entry that survives the trace pass).
+// The learner kernel's second evaluation -- same state, theta after the update -- re-reads only the tiles the filter
+// flags and keeps the first evaluation's products for the rest (a false positive is just a redundant load).
+#define BLOOM_WORDS 128
+__device__ __forceinline__ unsigned bloom_bit(int f) { return ((unsigned)f * 2654435761u) >> 20; }  // 12 bits
+__device__ __forceinline__ void bloom_set(unsigned* bl, int f) { const unsigned h = bloom_bit(f); atomicOr(&bl[h >> 5], 1u << (h & 31)); }
+__device__ __forceinline__ bool bloom_test(const unsigned* bl, int f) { const unsigned h = bloom_bit(f); return (bl[h >> 5] >> (h & 31)) & 1u; }
+
 // occ: the policy's bitmap in HBM; occ_s: its shared-memory copy for this step, or nullptr
 #ifdef RLM_TIMING
 __device__ long long g_tp_clk[8];
@@ -419,8 +427,12 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, const int* tt, int* t
   if (occ_s) ASSUME_SHARED(occ_s);
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];
+  unsigned* bloom = nullptr;
   if (tt) {
     ASSUME_SHARED(tt);
+    bloom = (unsigned*)ss;  // the small set is not needed on this path: its 512 bytes hold the filter
+    for (int i = lane; i < BLOOM_WORDS; i += 32) bloom[i] = 0u;
+    __syncwarp();
   } else {
     for (int i = lane; i < SS_SLOTS; i += 32) ss[i] = HS_EMPTY;
     __syncwarp();
@@ -466,6 +478,7 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, const int* tt, int* t
             __stcg(tf + pos, f);
             __stcg(te + pos, ev);
             red_add_f64(theta + f, scaled_update * (double)ev);
+            if (bloom) bloom_set(bloom, f);
           }
           w += __popc(mask);
         }
@@ -508,6 +521,7 @@ __device__ __noinline__ int trace_pass(AgentD& e, int* ss, const int* tt, int* t
         fresh = !(atomicOr(occ + (f >> 5), bit) & bit);
       }
       red_add_f64(theta + f, scaled_update * (double)1.0f);
+      if (bloom) bloom_set(bloom, f);
     }
     const int n_fresh = __popc(__ballot_sync(FULL, fresh));
     if (lane == 0) e.n_occ += n_fresh;

@@ -767,8 +767,11 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
 __host__ __device__ inline size_t a3_occ_offset(int is_double) {  // bytes from `sb` to the staged bitmap
   return ((size_t)A3_V + (size_t)(is_double ? 2 : 1) * 4 * RLM_MAX_ACTIONS * VROW * 8 + 15) & ~(size_t)15;
 }
+__host__ __device__ inline size_t a3_tt_offset(int is_double, int occ_smem_words) {  // bytes from `sb` to the tile table
+  return a3_occ_offset(is_double) + (((size_t)occ_smem_words * 4 + 15) & ~(size_t)15);
+}
 size_t rlm_agent3_smem_bytes(int is_double, int occ_smem_words) {
-  return AG_BYTES + a3_occ_offset(is_double) + (((size_t)occ_smem_words * 4 + 15) & ~(size_t)15);
+  return AG_BYTES + a3_tt_offset(is_double, occ_smem_words) + (size_t)2 * TT_SLOTS * 4;
 }
 
 // indices of lane j's tiles of group g for every action (registers), and the partial hash sum
@@ -824,6 +827,30 @@ __device__ __forceinline__ void a3_gather(const double* th_a, const double* th_b
       if (a < A) {
         Va[(RLM_MAX_ACTIONS + a) * VROW + lane] = w2 * va[a];
         if (th_b) Vb[(RLM_MAX_ACTIONS + a) * VROW + lane] = w2 * vb[a];
+      }
+    }
+  }
+}
+// Second evaluation of a step (same state, theta after this env's own update): only the tiles the update touched
+// -- flagged by the trace pass in `bloom` -- are read again; every other product row entry of V is still exact.
+__device__ __forceinline__ void a3_regather_patch(const double* th_a, const double* th_b, const unsigned* occ, bool occ_sm, const unsigned* bloom,
+                                                  const int* f, int g, int lane, double* V) {
+  const int A = P.n_actions;
+  const int seg0 = (g == 0) ? 0 : ((g == 1) ? 1 : 3);
+  const double w = P.gw[g], w2 = P.gw[2];
+  double* Va = V + (size_t)seg0 * RLM_MAX_ACTIONS * VROW;
+  double* Vb = V + (size_t)(A3_SEGS + seg0) * RLM_MAX_ACTIONS * VROW;
+#pragma unroll
+  for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+    if (a < A && bloom_test(bloom, f[a])) {
+      const bool nz = (occ == nullptr) || (occ_sm ? occ_test_s(occ, f[a]) : occ_test(occ, f[a]));
+      const double va = nz ? __ldcg(th_a + f[a]) : 0.0;
+      Va[a * VROW + lane] = w * va;
+      if (g == 1) Va[(RLM_MAX_ACTIONS + a) * VROW + lane] = w2 * va;
+      if (th_b) {
+        const double vb = nz ? __ldcg(th_b + f[a]) : 0.0;
+        Vb[a * VROW + lane] = w * vb;
+        if (g == 1) Vb[(RLM_MAX_ACTIONS + a) * VROW + lane] = w2 * vb;
       }
     }
   }
@@ -1007,8 +1034,8 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       __syncthreads();
       PH(4);
       if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); q_pre_a[lane] = qa; q_pre_b[lane] = qb; }
-      int* tt = (int*)V;  // the product rows are dead from here to the re-gather: the tile table lives there
-      __syncthreads();    // (warp 0 has read them)
+      int* tt = (int*)(sb + a3_tt_offset(P.is_double, P.occ_smem_words));
+      __syncthreads();
       PH(5);
       if (warp != 0) {
         // the two idle warps list every tile of the from-state with its last writer while warp 0 computes the TD error
@@ -1057,7 +1084,9 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
       if (stage == 0) {  // Q(from = to-state, .) under the UPDATED theta (serial.cpp:55,60); indices are still in registers
         __syncthreads();
         PH(9);
-        a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
+        // (the R-learning agents' extra evaluation has overwritten the product rows: gather everything again)
+        if (EXTRAS && P.algorithm >= RLM_ALGO_R_LEARN) a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
+        else a3_regather_patch(theta_a, theta_b, occ, occ_sm, (const unsigned*)sset, f, warp, lane, V);
         __syncthreads();
         PH(10);
         if (warp == 0 && lane < A) { double qa, qb; a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }

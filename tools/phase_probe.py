@@ -4,7 +4,8 @@ from rl_markets_b200 import abi, config, lib
 y = config.example_dict(**{"learning.memory_size": 65536, "learning.algorithm": "q_learn"})
 cfg = config.from_dict(y, n_envs=4096, flow_seed=1)
 m = lib.BatchedMarket(cfg)
-m.run_ticks(640); m.sync()
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 10): m.run_ticks(64)
+m.sync()
 m.run_ticks(1); m.sync()   # last launch's phases are what is read
 L = m.L
 clk = (C.c_longlong * (4096 * 16))(); sm = (C.c_uint * 4096)()
