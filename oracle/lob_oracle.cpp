@@ -1423,8 +1423,8 @@ void lobo_batch_apply(lobo_batch* b) {
 int64_t lobo_batch_steps(lobo_batch* b) { int64_t s = 0; for (auto* e : b->envs) s += e->total_steps; return s; }
 void lobo_batch_stats(lobo_batch* b, int32_t env, rlm_env_stats* out) { lobo_stats(b->envs[env], out); }
 
-int32_t lobo_to_ticks(const rlm_config* cfg, double px) { Venue v; v.init(cfg); return v.ToTicks(px); }
-double lobo_to_price(const rlm_config* cfg, int32_t ticks) { Venue v; v.init(cfg); return v.ToPrice(ticks); }
+int32_t lobo_to_ticks(const rlm_config* cfg, double px) { Venue v{}; v.init(cfg); return v.ToTicks(px); }
+double lobo_to_price(const rlm_config* cfg, int32_t ticks) { Venue v{}; v.init(cfg); return v.ToPrice(ticks); }
 double lobo_tick_size(const rlm_config* cfg, double px) { Venue v; v.init(cfg); return v.tick_size(px); }
 
 void lobo_tiles(const rlm_config* cfg, const float* vars, int32_t* out) {

@@ -387,7 +387,8 @@ __device__ __forceinline__ int tt_last_writer(const int* tt, int f) {
     slot = (slot + 1) & (TT_SLOTS - 1);
   }
 }
-// lanes of the building warps: thread t of n_threads inserts tiles t, t + n_threads, ... of the A*32 (tile j, action a)
+// building warps, thread t of n_threads: tt_build clears the slots; after a barrier among the builders, tt_fill
+// inserts tiles t, t + n_threads, ... of the A*32 (tile j, action a) of the from-state
 __device__ __forceinline__ void tt_build(int* tt, const AgentD& e, int t, int n_threads) {
   for (int i = t; i < 2 * TT_SLOTS; i += n_threads) tt[i] = (i < TT_SLOTS) ? HS_EMPTY : -1;
 }

@@ -1,21 +1,22 @@
-// rlm_kernels.cu -- sm_100a kernels of the batched LOB environment + tile-coded TD agent.
+// rlm_kernels.cu -- sm_100a kernels of the batched LOB environment + tile-coded TD agent (DESIGN.md section 3).
 //
-// Two kernels per market tick, tick-synchronous over all envs of the handle:
+// Two launches per market tick, tick-synchronous over all envs of the handle (the default engine):
 //
-//   rlm_env_kernel    one THREAD per env.  The env record (array-of-structs in HBM) is copied into a
-//                     thread-local EnvHdr -- local memory is lane-interleaved, so the scalar market
-//                     logic (Intraday::NextState, src/environment/intraday.cpp:224-272, and the rest of
-//                     rlm_env.cuh) runs SIMT over 32 envs with coalesced, L1-resident state.  An env
-//                     whose midprice moved (Base::performAction's do-while, base.cpp:285-305) finishes
-//                     the step, writes its state variables and reward, and appends itself to the ready
-//                     list with one warp-aggregated atomic.
-//   rlm_agent_kernel  one WARP per ready env (lane j = tiling j, N_TILINGS == 32 == warp width):
-//                     tile hashing, theta gathers, exact-order Q sums, the fused
-//                     trace-decay/clear/set/theta-update pass (Agent::HandleTransition,
-//                     src/rl/agent.cpp:86-101) and Q(from,.) for the next action selection.
+//   env tick     rlm_env_kernel_w: one WARP per env (B <= 16384) -- record staged in shared memory, Philox draws
+//                on three lanes, ask/bid book updates on two, rolling windows and state variables one per lane,
+//                the rest of the scalar market logic (Intraday::NextState, src/environment/intraday.cpp:224-272,
+//                and rlm_env.cuh) on lane 0.  rlm_env_kernel<32>: one THREAD per env (B > 16384), the record in
+//                lane-interleaved local memory, SIMT over 32 envs.  An env whose midprice moved
+//                (Base::performAction's do-while, base.cpp:285-305) finishes the step, writes its state
+//                variables and reward, and appends itself to the tick's ready list.
+//   learner step rlm_agent3_kernel: one CTA of three warps per ready env (warp g = feature group g, lane j =
+//                tiling j, N_TILINGS == 32 == warp width): tile hashing, theta gathers, exact-order Q sums, the
+//                fused trace-decay/clear/set/theta-update pass (Agent::HandleTransition, src/rl/agent.cpp:86-101)
+//                and Q(from,.) for the next action selection.  rlm_agent_kernel<8>: one warp per env (older).
 //
-// The next tick's rlm_env_kernel starts each stepped env with Learner::_step's action selection and
-// DoAction (serial.cpp:55-61, base.cpp:254-284), which is scalar work again.
+// The next tick's env kernel starts each stepped env with Learner::_step's action selection and DoAction
+// (serial.cpp:55-61, base.cpp:254-284), which is scalar work again.  rlm_run_kernel (persistent) and
+// rlm_fused_kernel are alternative single-launch engines, parity-green but slower (RLM_ENGINE=p|f).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #define RLM_TABLE_QUAL static __device__ const
@@ -25,7 +26,8 @@
 #include <cstdio>
 #include "rlm_kernels.h"
 
-// ---- agent-role shared memory: per warp [AgentD][scratch]  (the 8 KB hashing table is read through L1)
+// ---- one-warp-per-env learner (rlm_agent_kernel, fused and persistent engines): per warp [AgentD][scratch]
+// (the 8 KB hashing table is read through L1)
 // per-warp scratch: [q_pre_a, q_pre_b: 18 doubles][small set: 64 ints][vbuf: (1|2) * A_max * VROW doubles]
 #define SCR_Q 0
 #define SCR_SS (SCR_Q + 8 * 2 * RLM_MAX_ACTIONS)
@@ -1163,7 +1165,8 @@ cudaError_t rlm_launch_apply_dtheta(double* theta, double* dtheta, long long n, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused engine (default for independent policies): ONE launch, one warp per env for all `n_ticks` ticks.
+// Fused engine (RLM_ENGINE=f; not the default -- measured slower than two launches per tick):
+// ONE launch, one warp per env for all `n_ticks` ticks.
 // The env record stays in shared memory for the whole launch; the warp runs the tick (lane 0 scalar +
 // lane-parallel windows / state variables) and, whenever its env's midprice has moved, the learner step
 // inline -- so envs never wait for each other and the theta gathers of some warps overlap the book
