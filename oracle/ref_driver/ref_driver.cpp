@@ -142,13 +142,15 @@ void usage() {
           "usage: ref_driver --config cfg.yaml --symbol AAL.L --md md.csv --tas tas.csv\n"
           "                  [--algo q_learn|sarsa|double_q_learn] [--steps N] [--dump out.bin]\n"
           "                  [--theta out_theta.bin] [--quiet]\n"
-          "                  [--test-md md.csv --test-tas tas.csv --dump-test out.bin]   evaluation phase of main.cpp:216-241\n");
+          "                  [--test-md md.csv --test-tas tas.csv --dump-test out.bin]   evaluation phase of main.cpp:216-241\n"
+          "                  [--log-dir d]   evaluation phase writes d/profit_log.csv, d/order_log.csv (Backtester ctor) and\n"
+          "                                  d/test_stats.csv (env.writeStats, main.cpp:244)\n");
 }
 
 }  // namespace
 
 int main(int argc, char** argv) {
-  string cfg, symbol = "AAL.L", md, tas, algo, dump, theta_out, test_md, test_tas, dump_test;
+  string cfg, symbol = "AAL.L", md, tas, algo, dump, theta_out, test_md, test_tas, dump_test, log_dir;
   long max_steps = -1;
   bool quiet = false;
   for (int i = 1; i < argc; ++i) {
@@ -165,6 +167,7 @@ int main(int argc, char** argv) {
     else if (a == "--test-md") test_md = next();
     else if (a == "--test-tas") test_tas = next();
     else if (a == "--dump-test") dump_test = next();
+    else if (a == "--log-dir") log_dir = next();
     else if (a == "--quiet") quiet = true;
     else { usage(); return 2; }
   }
@@ -290,6 +293,15 @@ int main(int argc, char** argv) {
       m->GoGreedy();
       EnvSpy env2(c);
       env2.LoadData(symbol, test_md, test_tas);
+      if (!log_dir.empty()) {
+        // Backtester::Backtester, serial.cpp:97-119 (pattern "%v": main.cpp:254)
+        spdlog::set_pattern("%v");
+        spdlog::rotating_logger_mt("profit_log", log_dir + "/profit_log.csv", 1u << 30, 1);
+        spdlog::get("profit_log")->info("episode,step,action,position,midprice,spread,quoted_ask,quoted_bid,ask_level,bid_level,pnl_step,bandh_step");
+        spdlog::rotating_logger_mt("trade_log", log_dir + "/order_log.csv", 1u << 30, 1);
+        spdlog::get("trade_log")->info("episode,step,position,side,action,price,size,pnl");
+        env2.start_logging();
+      }
       rl::State b1(c), b2(c);  // Runner ctor, serial.cpp:9-16
       rl::State* bstate = &b1;
       rl::State* blast = &b2;
@@ -316,6 +328,11 @@ int main(int argc, char** argv) {
       }
       env2.ClearInventory();
       env2.fill(test_last);
+      if (!log_dir.empty()) {
+        spdlog::get("profit_log")->flush();
+        spdlog::get("trade_log")->flush();
+        env2.writeStats(log_dir + "/test_stats.csv");  // main.cpp:244
+      }
       if (ft2) fclose(ft2);
     }
 

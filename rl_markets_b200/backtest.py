@@ -27,8 +27,20 @@ def profit_rows(records, date):
                                          r.bid_quote, r.ask_level, r.bid_level, r.pnl_step, r.bandh_step))
 
 
+def test_stats_rows(records, market_sells, market_buys):
+    """The eight rows Base::writeStats leaves in test_stats.csv.  trade_stats.{ask,bid}_transactions are copied from the
+    books in Base::UpdateStats (base.cpp:412-417), which runs at the START of every step (base.cpp:278): what the file
+    shows is the count after the last-but-one step, one step behind the books.  market_* are bumped where the market
+    orders happen, the final ClearInventory included (base.cpp:339-349)."""
+    lag = records[-2] if len(records) >= 2 else None
+    return [("asks_placed", 0), ("bids_placed", 0), ("asks_cancelled", 0), ("bids_cancelled", 0),
+            ("ask_transactions", lag.ask_transactions if lag else 0), ("bid_transactions", lag.bid_transactions if lag else 0),
+            ("market_sells", market_sells), ("market_buys", market_buys)]
+
+
 def write_logs(market, out_dir, env=0, date=20100104):
-    """Write profit_log.csv / test_stats.csv / theta.bin for recorded env `env` of a handle in backtest mode."""
+    """Write profit_log.csv / test_stats.csv / theta.bin for recorded env `env` of a handle in backtest mode
+    (every step of the episode must be recorded: cfg.record_cap >= steps)."""
     os.makedirs(out_dir, exist_ok=True)
     recs, _keep = market.records(env)
     paths = {k: os.path.join(out_dir, v) for k, v in
@@ -39,9 +51,7 @@ def write_logs(market, out_dir, env=0, date=20100104):
             f.write(row + "\n")
     st = market.stats(env, 1)[0]
     with open(paths["test_stats"], "w") as f:
-        for k, v in (("asks_placed", 0), ("bids_placed", 0), ("asks_cancelled", 0), ("bids_cancelled", 0),
-                     ("ask_transactions", st.ask_transactions), ("bid_transactions", st.bid_transactions),
-                     ("market_sells", st.market_sells), ("market_buys", st.market_buys)):
+        for k, v in test_stats_rows(recs, st.market_sells, st.market_buys):
             f.write("%s,%d\n" % (k, v))
     with open(paths["theta"], "wb") as f:
         f.write(bytes(market.theta(env)))

@@ -126,7 +126,7 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int n_ticks;
   int stream_ticks;   // ticks in the resident stream chunk
   int stream_off;     // first tick of the chunk this launch consumes
-  int tick_sync;      // persistent engine: 1 = CTA barrier per tick (keeps the CTA's warps on the same code)
+  int reserved0;      // (was a per-tick CTA barrier switch of the persistent engine; unused)
   int backtest;       // 1: Backtester::_step (serial.cpp:121-137): act on the current state, never learn
 };
 

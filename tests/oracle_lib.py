@@ -187,6 +187,9 @@ def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=
             subprocess.check_call([FLOW_CSV, "--seed", str(test["flow_seed"]), "--env", str(test["env"]), "--ticks",
                                    str(test["ticks"]), "--dt-ms", str(dt_ms), "--md", md2, "--tas", tas2] + t02)
             cmd += ["--test-md", md2, "--test-tas", tas2, "--dump-test", dump2]
+            if test.get("logs"):
+                os.makedirs(os.path.join(d, "logs"))
+                cmd += ["--log-dir", os.path.join(d, "logs")]
         out = subprocess.check_output(cmd)
         summary = json.loads(out.decode().strip().splitlines()[-1])
         raw = open(dump, "rb").read()
@@ -200,11 +203,13 @@ def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=
             for i in range(0, len(tr), 16):
                 idx, val = struct.unpack("<qd", tr[i:i + 16])
                 theta[idx] = val
-        test_records = None
+        test_records, logs = None, None
+        if test and test.get("logs"):
+            logs = {n: open(os.path.join(d, "logs", n)).read() for n in ("profit_log.csv", "test_stats.csv", "order_log.csv")}
         if test:
             raw2 = open(dump2, "rb").read()
             n2 = len(raw2) // C.sizeof(abi.StepRecord)
             recs2 = (abi.StepRecord * n2).from_buffer_copy(raw2)
             test_records = [recs2[i] for i in range(n2)]
     return {"records": [recs[i] for i in range(n)], "summary": summary, "theta": theta, "_keep": recs,
-            "test_records": test_records}
+            "test_records": test_records, "logs": logs}

@@ -72,7 +72,10 @@ def test_backtest_logs(rlm, tmp_path):
     # Base::writeStats (base.cpp:451-456) reopens the file for each writer: only TradeStatistics survives
     assert list(stats) == ["asks_placed", "bids_placed", "asks_cancelled", "bids_cancelled", "ask_transactions",
                            "bid_transactions", "market_sells", "market_buys"]
-    assert int(stats["ask_transactions"]) == st.ask_transactions and int(stats["market_buys"]) == st.market_buys
+    assert int(stats["ask_transactions"]) == recs[-2].ask_transactions and int(stats["market_buys"]) == st.market_buys
+    # and the files are, byte for byte, what the reference itself wrote for this case (tools/make_golden.py)
+    assert open(out["profit_log"]).read() == open(os.path.join(G.GOLD, case["name"] + "_profit_log.csv")).read()
+    assert open(out["test_stats"]).read() == open(os.path.join(G.GOLD, case["name"] + "_test_stats.csv")).read()
     assert os.path.getsize(out["theta"]) == 8 * m.cfg.memory_size
     m.close()
 

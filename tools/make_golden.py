@@ -5,6 +5,7 @@ which has no reference tree, can check against them).
 
   tests/golden/units.json          reference unit-level vectors (oracle/_ref/ref_units)
   tests/golden/steps_<name>.bin    first N rlm_step_record of a reference run (oracle/_ref/ref_driver)
+  tests/golden/bt_*_{profit_log,test_stats}.csv   the reference's own evaluation logs for the backtest cases
   tests/golden/manifest.json       the configs that produced them
 """
 import ctypes as C
@@ -84,7 +85,11 @@ def main():
         cfg = config.from_dict(y)
         t0 = day_t0(cfg, c["train_open_ticks"])
         test = dict(c["test"], t0_ms=day_t0(cfg, c["test"]["open_ticks"]))
-        ref = ol.run_ref(y_run, c["flow_seed"], c["env"], c["ticks"], t0_ms=t0, test=test)
+        ref = ol.run_ref(y_run, c["flow_seed"], c["env"], c["ticks"], t0_ms=t0, test=dict(test, logs=True))
+        # the evaluation logs as the reference itself writes them (Backtester's profit_log, Base::writeStats)
+        for fname in ("profit_log.csv", "test_stats.csv"):
+            with open(os.path.join(GOLD, "%s_%s" % (c["name"], fname)), "w") as f:
+                f.write(ref["logs"][fname])
         assert ref["summary"]["terminal"] == 1
         for suffix, recs in (("", ref["records"]), ("_test", ref["test_records"])):
             with open(os.path.join(GOLD, "steps_%s%s.bin" % (c["name"], suffix)), "wb") as f:
