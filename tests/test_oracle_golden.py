@@ -152,20 +152,30 @@ def test_generators(oracle):
     assert [c for c in G.units()["rng"]["cases"] if c["seed"] == 1994][0]["rand"][:3] == [1261852369, 322867519, 980044188]
 
 
-def test_live_reference_when_built(oracle):
-    """In the build container the restatement is also checked against a fresh run of oracle/_ref."""
+_LIVE = [
+    ("double_q_learn", 8192, 31, {}),
+    ("online_r_learn", 5003, 7, {"policy.eps_init": 0.2, "learning.beta": 0.02}),
+    ("r_learn", 4096, 11, {"policy.type": "boltzmann", "policy.tau_init": 0.08, "policy.tau_floor": 0.01, "policy.tau_T": 10}),
+    ("sarsa", 8192, 5, {"reward.measure": "pnl", "data.symbols": ["NOKIA.HE"], "learning.random_init": True}),
+]
+
+
+@pytest.mark.parametrize("algo,M,seed,over", _LIVE)
+def test_live_reference_when_built(oracle, algo, M, seed, over):
+    """In the build container the restatement is also checked against fresh runs of oracle/_ref (new seeds, the
+    R-learning agents, Boltzmann, another venue's tick table and hours, random initial weights)."""
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not present on this machine; golden fixtures cover it")
-    y = config.example_dict(**{"learning.memory_size": 8192, "learning.algorithm": "double_q_learn", "debug.random_seed": 31})
+    y = config.example_dict(**{"learning.memory_size": M, "learning.algorithm": algo, "debug.random_seed": seed, **over})
     cfg = config.from_dict(y, flow_seed=123)
     ticks = oracle.lib_generate(cfg, 0, 4000)
     port = oracle.run_port(cfg, 0, ticks)
-    ref = oracle.run_ref(y, 123, 0, 4000, want_theta=True)
+    ref = oracle.run_ref(y, 123, 0, 4000, want_theta=True, t0_ms=cfg.flow.t0_ms)
     n = min(len(ref["records"]), port["steps"])
     assert n > 800
     for i in range(n):
         bad = abi.record_fields_equal(ref["records"][i], port["records"][i])
-        assert not bad, "step %d: %r" % (i, G.describe_diff(ref["records"][i], port["records"][i], bad))
+        assert not bad, "%s step %d: %r" % (algo, i, G.describe_diff(ref["records"][i], port["records"][i], bad))
 
 
 def test_book_scenarios(oracle):
