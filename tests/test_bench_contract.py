@@ -1,0 +1,55 @@
+"""The JSON line bench.py prints is a contract with the driver: check the committed round-1 lines against it, and
+that the reference arm (which needs no GPU) still produces a conforming line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(ROOT, "profiles")
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config"}
+
+
+def _line(name):
+    return json.loads(open(os.path.join(PROF, name)).read().strip().splitlines()[-1])
+
+
+def test_committed_headline_line_has_every_contract_key():
+    d = _line("bench_r1_final_c1.json")
+    assert BASE_KEYS <= set(d) and {"roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"} <= set(d)
+    assert d["metric"].startswith("env steps/sec") and d["unit"] == "env_steps/s" and d["n_gpus"] == 1
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert "workload" in d["config"] and d["config"]["workload"].startswith("C1") and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 4096 * 128 and e["d2h_bytes_per_step"] == 4096 * 8
+    assert e["value"] != d["value"], "the end-to-end figure must be measured, not copied"
+    assert d["gpu_launches"] >= 2 * 64 * d["steps"]  # two kernels per tick, 64 ticks per bench step
+    assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.9 * d["clocks"]["sm_max_mhz"]
+    # the timed region is the long-run state; the cold-start figure is reported beside it, never as `value`
+    assert d["config"]["pretrain_ticks"] > 0 and d["cold_start"]["value"] > d["value"]
+
+
+def test_committed_scaling_and_reference_lines():
+    two = _line("bench_r1_final_c1_2gpu.json")
+    one = _line("bench_r1_final_c1.json")
+    assert two["n_gpus"] == 2 and 1.8 < two["value"] / one["value"] < 2.2
+    ref = _line("bench_r1_final_c1_reference_arm.json")
+    assert ref["impl"] == "reference" and BASE_KEYS <= set(ref)
+    assert ref["e2e"]["value"] == ref["value"] and ref["e2e"]["h2d_bytes_per_step"] == 0
+    assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["cores"] >= 1
+
+
+def test_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` times the reference's CPU loop (oracle/_ref when built, else the oracle port)."""
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                                   "--warmup", "0", "--ref-ticks", "10000"], timeout=600)
+    d = json.loads(out.decode().strip().splitlines()[-1])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 1e3
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
