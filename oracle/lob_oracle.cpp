@@ -1322,10 +1322,13 @@ int64_t lobo_sum_traces(lobo_env* e) { return e->sum_traces; }
 const double* lobo_theta(lobo_env* e, int table) { return table == 0 ? e->theta.data() : (e->theta_b.empty() ? nullptr : e->theta_b.data()); }
 double lobo_rho(lobo_env* e) { return e->rho; }
 void lobo_handle_terminal(lobo_env* e, int episode) { e->HandleTerminal(episode); }
-// next episode on a FRESH experiment::serial::Learner (never-populated States, serial.cpp:9-16): Intraday::Initialise
-// + rewound data.  (A Learner reused across episodes would carry a stale State over, src/main.cpp:48-58; that
-// carry-over is not part of rlm_reset's contract.)
-void lobo_reset(lobo_env* e) {
+// next episode of the SAME experiment::serial::Learner (src/main.cpp:47-58: one `experiment` object per training thread):
+// Intraday::Initialise + rewound data.  The two State objects of Runner (serial.h:17-23) are NOT re-created, so the
+// first action of the new episode is chosen from -- and the first transition starts at -- the State that was the
+// from-state of the previous episode's last completed transition (serial.cpp:24-25,55,60): kept as is.
+void lobo_reset(lobo_env* e) { e->reset_episode(); }
+// a FRESH Learner (never-populated States, serial.cpp:9-16) on the same env and agent
+void lobo_reset_fresh_learner(lobo_env* e) {
   e->state1.init(e->c.memory_size, e->c.n_actions, e->c.n_tilings);
   e->state2.init(e->c.memory_size, e->c.n_actions, e->c.n_tilings);
   e->state = &e->state1; e->last_state = &e->state2;

@@ -142,6 +142,8 @@ void usage() {
           "usage: ref_driver --config cfg.yaml --symbol AAL.L --md md.csv --tas tas.csv\n"
           "                  [--algo q_learn|sarsa|double_q_learn] [--steps N] [--dump out.bin]\n"
           "                  [--theta out_theta.bin] [--quiet]\n"
+          "                  [--episodes N]   N training episodes on ONE Intraday + ONE Learner-equivalent (the States and the\n"
+          "                                   agent are reused, LoadData + RunEpisode per episode: main.cpp:45-60, serial.cpp:72-95)\n"
           "                  [--test-md md.csv --test-tas tas.csv --dump-test out.bin]   evaluation phase of main.cpp:216-241\n"
           "                  [--log-dir d]   evaluation phase writes d/profit_log.csv, d/order_log.csv (Backtester ctor) and\n"
           "                                  d/test_stats.csv (env.writeStats, main.cpp:244)\n");
@@ -152,6 +154,7 @@ void usage() {
 int main(int argc, char** argv) {
   string cfg, symbol = "AAL.L", md, tas, algo, dump, theta_out, test_md, test_tas, dump_test, log_dir;
   long max_steps = -1;
+  int n_episodes = 1;
   bool quiet = false;
   for (int i = 1; i < argc; ++i) {
     string a = argv[i];
@@ -168,6 +171,7 @@ int main(int argc, char** argv) {
     else if (a == "--test-tas") test_tas = next();
     else if (a == "--dump-test") dump_test = next();
     else if (a == "--log-dir") log_dir = next();
+    else if (a == "--episodes") n_episodes = atoi(next().c_str());
     else if (a == "--quiet") quiet = true;
     else { usage(); return 2; }
   }
@@ -217,8 +221,9 @@ int main(int argc, char** argv) {
     rl::Agent* m = av.agent;
 
     EnvSpy env(c);
-    env.LoadData(symbol, md, tas);
 
+    // experiment::serial::Runner::Runner (serial.cpp:9-16): ONE pair of States for every episode of this driver, exactly
+    // like `experiment::serial::Learner experiment(c, env)` of main.cpp:47-48 lives across the while(true) of train()
     rl::State state1(c), state2(c);
     rl::State* state = &state1;
     rl::State* last_state = &state2;
@@ -228,57 +233,64 @@ int main(int argc, char** argv) {
 
     auto t_start = chrono::steady_clock::now();
 
-    // Runner::RunEpisode, serial.cpp:18-34
-    env.resetStats();  // Learner::RunEpisode, serial.cpp:75
-    if (!env.Initialise()) throw runtime_error("Initialise() failed: not enough data");
-    last_state->newState(env);
-
     long steps = 0;
     double sum_reward = 0.0;
     long hist[16] = {0};
     bool terminal = false;
-    while (true) {
-      // Learner::_step, serial.cpp:53-70
-      swap(state, last_state);
-      if (env.isTerminal()) { terminal = true; break; }
-      int action = m->action(*last_state);
-      if (!env.performAction(action)) { terminal = true; break; }
-      state->newState(env);
-      double reward = env.getReward();
-      m->HandleTransition(*last_state, action, reward, *state);
+    for (int episode = 0; episode < n_episodes; ++episode) {
+      env.LoadData(symbol, md, tas);  // main.cpp:55 (the same day again: what rlm_reset's rewound stream stands for)
+      // Learner::RunEpisode serial.cpp:72-76, Runner::RunEpisode serial.cpp:18-34
+      env.resetStats();
+      if (!env.Initialise()) throw runtime_error("Initialise() failed: not enough data");
+      last_state->newState(env);
 
-      sum_reward += reward;
-      if (action >= 0 && action < 16) hist[action]++;
+      long ep_steps = 0;
+      terminal = false;
+      while (true) {
+        // Learner::_step, serial.cpp:53-70
+        swap(state, last_state);
+        if (env.isTerminal()) { terminal = true; break; }
+        int action = m->action(*last_state);
+        if (!env.performAction(action)) { terminal = true; break; }
+        state->newState(env);
+        double reward = env.getReward();
+        m->HandleTransition(*last_state, action, reward, *state);
 
-      if (fd) {
-        rlm_step_record r;
-        memset(&r, 0, sizeof(r));
-        r.step = (int32_t)steps;
-        r.action = action;
-        env.fill(r);
-        r.reward = reward;
-        auto& sv = state->toVector();
-        r.n_state = (int32_t)sv.size();
-        for (size_t i = 0; i < sv.size() && i < RLM_N_STATE_MAX; ++i) r.state[i] = sv[i];
-        r.delta = av.delta();
-        rl::Traces* tr = av.traces();
-        double* th = av.theta();
-        r.n_traces = tr->n_nonzero_traces;
-        uint64_t h = 0;
-        for (int k = 0; k < tr->n_nonzero_traces; ++k) {
-          int f = tr->nonzero_traces[k];
-          h += rlm_trace_mix((uint32_t)f, bits_of(tr->eligibility[f]), bits_of(th[f]));
+        sum_reward += reward;
+        if (action >= 0 && action < 16) hist[action]++;
+
+        if (fd) {
+          rlm_step_record r;
+          memset(&r, 0, sizeof(r));
+          r.step = (int32_t)ep_steps;
+          r.action = action;
+          env.fill(r);
+          r.reward = reward;
+          auto& sv = state->toVector();
+          r.n_state = (int32_t)sv.size();
+          for (size_t i = 0; i < sv.size() && i < RLM_N_STATE_MAX; ++i) r.state[i] = sv[i];
+          r.delta = av.delta();
+          rl::Traces* tr = av.traces();
+          double* th = av.theta();
+          r.n_traces = tr->n_nonzero_traces;
+          uint64_t h = 0;
+          for (int k = 0; k < tr->n_nonzero_traces; ++k) {
+            int f = tr->nonzero_traces[k];
+            h += rlm_trace_mix((uint32_t)f, bits_of(tr->eligibility[f]), bits_of(th[f]));
+          }
+          r.trace_hash = h;
+          fwrite(&r, sizeof(r), 1, fd);
         }
-        r.trace_hash = h;
-        fwrite(&r, sizeof(r), 1, fd);
-      }
 
-      ++steps;
+        ++steps;
+        ++ep_steps;
+        if (max_steps >= 0 && steps >= max_steps) break;
+      }
+      if (terminal) {
+        env.ClearInventory();              // serial.cpp:31
+        m->HandleTerminal(episode);        // serial.cpp:79: HandleTerminal(_episode_counter++)
+      }
       if (max_steps >= 0 && steps >= max_steps) break;
-    }
-    if (terminal) {
-      env.ClearInventory();              // serial.cpp:31
-      m->HandleTerminal(0);              // serial.cpp:79
     }
     auto t_end = chrono::steady_clock::now();
     double secs = chrono::duration<double>(t_end - t_start).count();

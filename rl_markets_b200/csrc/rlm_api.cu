@@ -40,7 +40,7 @@ struct rlm_handle_s {
   int engine = 1;        // 1 tick-synchronous (two launches per tick), 0 persistent queue (rlm_run_kernel), 2 fused (warp per env)
   int n_agent_ctas = 0;  // persistent engine: CTAs in the agent role
   int env_variant = 0;   // env tick kernel: 0 = warp per env, 1 = thread per env
-  int agent_variant = 3; // agent kernel: 3 = three warps per env, 1 = one warp per env
+  int agent_variant = 4; // learner kernel: 4 = rlm_learn_kernel (one warp per env, round 2), 3 = three warps per env, 1 = round-1 one-warp kernel
   unsigned* d_qctl = nullptr;  // [4]: q_head, q_tail, env_warps_done, q_done
   DynParams shared_dyn;
   bool in_run = false;
@@ -141,11 +141,15 @@ static int derive(rlm_handle_s* h) {
   if (c.memory_size == 1) p.m_magic = ~0ull;
   for (int a = 0; a < RLM_MAX_ACTIONS; ++a)  // hash_UNH term of the action integer for feature group 0 (3 floats + tiling + int)
     p.ra_m[a] = (int)((unsigned long long)rlm_rndseq_table[(a + 449 * 4) & 2047] % (unsigned long long)c.memory_size);
+  for (int g = 0; g < 3; ++g) {
+    const int nf = (g == 0) ? 3 : ((g == 1) ? c.n_state_vars - 3 : c.n_state_vars);
+    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) p.rg[g][a] = rlm_rndseq_table[(g * c.n_actions + a + 449 * (nf + 1)) & 2047];
+  }
   p.scratch_bytes = (int)rlm_scratch_bytes(p.is_double);
   p.occ_words = (int)((c.memory_size + 31) / 32);
   // independent policies with a bitmap of <= 16 KB (memory_size <= 2^17): the 3-warp learner kernel keeps the env's
   // bitmap in shared memory for the step, so the 1728 bit tests never touch the global load path
-  p.occ_smem_words = (!c.shared_policy && (size_t)p.occ_words * 4 <= 16384 && (p.occ_words & 3) == 0) ? p.occ_words : 0;  // (16-byte copies)
+  p.occ_smem_words = 0;  // round 2: the bitmap is maintained by the fallback kernels but never consulted
   p.gl = (float)(c.gamma * c.lambda);  // Traces::decay(float rate) narrows gamma*lambda (A11)
   for (int i = 0; i < 3; ++i) p.gw[i] = c.group_weights[i];
   p.gamma = c.gamma;
@@ -214,7 +218,11 @@ static int derive(rlm_handle_s* h) {
 }
 
 static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tslot, int stage) {
-  if (h->agent_variant == 3) {
+  // Q-learning / SARSA / Double-Q training: the one-warp-per-env learner (rlm_learn.cuh).  The R-learning agents' third
+  // evaluation and the backtest step stay on the three-warp kernel's EXTRAS instantiation.
+  if (h->agent_variant == 4 && !d.backtest && h->cfg.algorithm < RLM_ALGO_R_LEARN)
+    return rlm_launch_learn(h->ptr, d, h->cfg.n_envs, h->hp.is_double, tslot, h->n_sms, stage, h->stream);
+  if (h->agent_variant >= 3) {
     const int full = (d.backtest || h->cfg.algorithm >= RLM_ALGO_R_LEARN) ? 1 : 0;
     return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, h->hp.occ_smem_words, tslot, h->n_sms, stage, full, h->stream);
   }
@@ -318,12 +326,14 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     int cap = resident - std::min(n_env_ctas, std::max(resident / 4, 1));
     h->n_agent_ctas = std::max(1, std::min(want, cap));
     if (const char* s = getenv("RLM_AGENT_CTAS")) { int v = atoi(s); if (v > 0 && v < resident) h->n_agent_ctas = v; }
-    if (const char* s = getenv("RLM_ENGINE")) h->engine = (s[0] == 'p') ? 0 : ((s[0] == 'f') ? 2 : 1);
+    // engines: 's' tick-synchronous (two launches per tick), 'F' fused persistent round-2 kernel, 'f' round-1 fused kernel,
+    // 'p' persistent queue
+    if (const char* s = getenv("RLM_ENGINE")) h->engine = (s[0] == 'p') ? 0 : ((s[0] == 'f') ? 2 : ((s[0] == 'F') ? 3 : 1));
     // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
     h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
     if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
     if (const char* s = getenv("RLM_PDL")) rlm_set_pdl(atoi(s));  // programmatic dependent launch of the per-tick kernels (default off: slower when measured)
-    if (const char* s = getenv("RLM_AGENT_VARIANT")) h->agent_variant = (atoi(s) == 1) ? 1 : 3;
+    if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
@@ -378,7 +388,7 @@ int rlm_reset(rlm_handle h) {
 int rlm_set_mode(rlm_handle h, int32_t mode) {
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   if (mode != RLM_MODE_TRAIN && mode != RLM_MODE_BACKTEST) return fail(RLM_ERR_INVALID_ARGUMENT, "unknown mode");
-  if (mode == RLM_MODE_BACKTEST && h->engine != 1) return fail(RLM_ERR_UNSUPPORTED, "backtest mode runs on the tick-synchronous engine only");
+  if (mode == RLM_MODE_BACKTEST && h->engine != 1 && h->engine != 3) return fail(RLM_ERR_UNSUPPORTED, "backtest mode runs on the tick-synchronous engine only");
   if (mode == RLM_MODE_BACKTEST && h->cfg.shared_policy) return fail(RLM_ERR_UNSUPPORTED, "backtest mode with shared_policy is not built");
   h->dyn.backtest = mode;
   return RLM_OK;
@@ -478,6 +488,12 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
   }
   if (h->engine == 2) {
     CK(rlm_launch_fused(h->ptr, d, h->cfg.n_envs, h->hp.is_double, h->stream));
+    h->launches += 1;
+    return RLM_OK;
+  }
+  if (h->engine == 3 && !d.backtest && h->cfg.algorithm < RLM_ALGO_R_LEARN) {
+    // fused persistent engine, round 2 (rlm_fused2_kernel): one launch, no per-tick barrier
+    CK(rlm_launch_fused2(h->ptr, d, h->cfg.n_envs, h->hp.is_double, h->stream));
     h->launches += 1;
     return RLM_OK;
   }

@@ -90,7 +90,13 @@ __global__ void rlm_init_kernel(DevPtrs ptr, int mode) {
   e->last_date = 0; e->date = 0; e->time_ms = 0;
   e->phase = PH_PREOPEN;
   e->ag.ep_step = 0;
-  e->ag.null_from = 1;
+  if (mode == 1) {  // same Learner, next episode: the stale State is the from-state of the last completed transition
+    for (int i = 0; i < RLM_N_STATE_MAX + 3; ++i) e->ag.from_vars[i] = e->ag.prev_vars[i];
+    e->ag.null_from = e->ag.prev_null;
+  } else {  // (mode 0: AgentD was zeroed above; mode 2: a new Runner's States are never-populated, serial.cpp:9-16)
+    e->ag.null_from = 1;
+    e->ag.prev_null = 1;
+  }
   e->ag.need_begin = 0;
   e->ag.kind = 0;
   rlm_flow_init(&e->flow, &P.flow, (uint64_t)(P.env_index0 + b));
@@ -345,37 +351,137 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
 // lanes 0..7 each evaluate one state variable at a step end.  No env waits for another one: a warp whose
 // env needs the learner step just appends it to the ready list.
 #define ENVW_WARPS 8
+// per-warp shared memory of the tick: [EnvHdr][message 128][pushv, oldv: 2 x 10 doubles][flag 16, Philox 48, fills + errs 64]
+__host__ __device__ inline size_t envw_hdr_bytes() { return (sizeof(EnvHdr) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t envw_warp_bytes() { return envw_hdr_bytes() + 128 + 8 * 2 * RLM_NWIN + 128; }
+struct EnvWarp {
+  EnvHdr* e; rlm_tick_msg* msg; double* pushv; double* oldv; int* flag; unsigned* r12; Fill* fills;
+};
+__device__ __forceinline__ EnvWarp envw_carve(unsigned char* wbase) {
+  EnvWarp w;
+  const size_t hb = envw_hdr_bytes();
+  w.e = (EnvHdr*)wbase;
+  w.msg = (rlm_tick_msg*)(wbase + hb);
+  w.pushv = (double*)(wbase + hb + 128);
+  w.oldv = w.pushv + RLM_NWIN;
+  w.flag = (int*)(w.oldv + RLM_NWIN);
+  w.r12 = (unsigned*)(w.flag + 4);
+  w.fills = (Fill*)(w.r12 + 12);  // 2 Fill + 2 ints
+  return w;
+}
+// env record HBM <-> shared memory, coalesced 16-byte copies; the loads of one record are all in flight together
+__device__ __forceinline__ void envw_stage_in(EnvHdr* dst_e, const EnvHdr* g, int lane) {
+  const int4* src = (const int4*)g;
+  int4* dst = (int4*)dst_e;
+  const int n16 = (int)(envw_hdr_bytes() / 16);
+  static_assert(sizeof(EnvHdr) <= 4 * 32 * 16, "four 16-byte loads per lane cover the env header");
+  int4 t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < n16) t[k] = src[i]; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < n16) dst[i] = t[k]; }
+}
+__device__ __forceinline__ void envw_stage_out(EnvHdr* g, const EnvHdr* src_e, int lane) {
+  int4* dst = (int4*)g;
+  const int4* src = (const int4*)src_e;
+  for (int i = lane; i < (int)(envw_hdr_bytes() / 16); i += 32) dst[i] = src[i];
+}
+
+// One market tick of the env staged in `w`, by its warp.  stream_pos: index of this tick in the resident stream chunk.
+// Returns -1, or the ready kind (0: a learner step ended -- state variables and reward are in e.ag; 1: warm-up ended).
+__device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const DevPtrs& ptr, const DynParams& D, int env, int stream_pos, int lane,
+                                         unsigned& ticked) {
+  EnvHdr& e = *w.e;
+  rlm_tick_msg& msg = *w.msg;
+  double* pushv = w.pushv;
+  double* oldv = w.oldv;
+  int ready = -1;
+  bool have = true;
+  if (P.source == RLM_SOURCE_GENERATOR) {
+    flow_next_warp(&e.flow, &msg, w.r12, lane);
+  } else {
+    if (stream_pos >= D.stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; have = false; }
+    else ((unsigned*)&msg)[lane] = __ldg((const unsigned*)(ptr.stream + ((size_t)stream_pos * P.n_envs + env)) + lane);
+  }
+  if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);  // issued early, consumed after the book logic
+  __syncwarp();
+  const int phase = e.phase;
+  if (have && phase == PH_PREOPEN) {  // intraday.cpp:111-116
+    if (lane == 0) {
+      msg.n_tx = 0;
+      update_book_profiles(e, msg);
+      if (market_is_open(e)) e.phase = PH_WARMUP;
+    }
+  } else if (have) {
+    ticked += 1;
+    if (lane == 0 && phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
+    __syncwarp();
+    next_state_warp(e, msg, pushv, w.fills, lane);  // Intraday::NextState, ask side on lane 0, bid side on lane 1
+    __syncwarp();
+    if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
+    __syncwarp();
+    if (lane == 0) {
+      int r = -1;
+      e.tp_val = e.w_mean[W_TP];
+      if (phase == PH_WARMUP) {  // intraday.cpp:118-135
+        bool full = true;
+        for (int k = 0; k < 8; ++k) full = full && (e.w_count[k] == P.win_size[k]);
+        if (full) {
+          place_orders(e, 1, 1);
+          e.phase = PH_RUN;
+          e.ag.kind = 1;  // serial.cpp:24-25,55-60: the first from-state is the never-populated (or the stale) State
+          r = 1;
+        }
+      } else {
+        // tail of one iteration of performAction's do-while (base.cpp:292-305)
+        double mpm = m_midprice(e) - m_last_midprice(e);
+        e.pnl_step += (double)e.position * mpm;
+        e.momentum_pnl_step += (double)e.position * mpm;
+        e.agg_r += get_reward(e);
+        e.agg_pnl += e.pnl_step;
+        e.agg_mpm += mpm;
+        if (!(!is_terminal(e) && fabs(e.agg_mpm) < 1e-5)) {
+          e.pnl_step = e.agg_pnl;  // base.cpp:317-331
+          pushv[W_PNLUP] = fmax(0.0, e.pnl_step);
+          pushv[W_PNLDN] = fabs(fmin(0.0, e.pnl_step));
+          e.ep_reward += e.agg_r;
+          e.ep_bandh += e.agg_mpm;
+          r = 0;
+        }
+      }
+      *w.flag = r;
+    }
+    __syncwarp();
+    ready = *w.flag;
+    if (ready == 0) {
+      if (lane == W_PNLUP || lane == W_PNLDN) window_push(e, ring, lane, pushv[lane], oldv[lane]);
+      __syncwarp();
+      // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
+      if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
+      if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
+    } else if (ready == 1 && D.backtest) {
+      // Backtester::_step builds its state from the env before every action (serial.cpp:126), the first one included
+      if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
+    }
+  }
+  __syncwarp();
+  return ready;
+}
+
 __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr, DynParams D, int tslot, int only_begin) {
   PDL_PROLOGUE();
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int env = blockIdx.x * ENVW_WARPS + warp;
   if (env >= P.n_envs) return;
-  const int hdr_bytes = (int)((sizeof(EnvHdr) + 15) & ~(size_t)15);
-  unsigned char* wbase = smem + (size_t)warp * (hdr_bytes + 128 + 8 * 2 * RLM_NWIN + 128);
-  EnvHdr& e = *(EnvHdr*)wbase;
-  rlm_tick_msg& msg = *(rlm_tick_msg*)(wbase + hdr_bytes);
-  double* pushv = (double*)(wbase + hdr_bytes + 128);
-  double* oldv = pushv + RLM_NWIN;
-  int* flag = (int*)(oldv + RLM_NWIN);
-  unsigned* r12 = (unsigned*)(flag + 4);
-  Fill* fills = (Fill*)(r12 + 12);  // 2 Fill + 2 ints
+  const EnvWarp w = envw_carve(smem + (size_t)warp * envw_warp_bytes());
+  EnvHdr& e = *w.e;
   EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
   double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
-  {
-    // the trailing begin-only pass touches few envs: look before staging.  A tick pass stages straight away -- one
-    // memory round trip instead of two on every env's critical path -- and drops finished envs afterwards.
-    if (only_begin && !g->ag.need_begin) return;
-    const int4* src = (const int4*)g;
-    int4* dst = (int4*)&e;
-    const int n16 = hdr_bytes / 16;
-    static_assert(sizeof(EnvHdr) <= 4 * 32 * 16, "four 16-byte loads per lane cover the env header");
-    int4 t[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < n16) t[k] = src[i]; }  // all in flight together
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < n16) dst[i] = t[k]; }
-  }
+  // the trailing begin-only pass touches few envs: look before staging.  A tick pass stages straight away -- one
+  // memory round trip instead of two on every env's critical path -- and drops finished envs afterwards.
+  if (only_begin && !g->ag.need_begin) return;
+  envw_stage_in(&e, g, lane);
   __syncwarp();
   if (e.phase == PH_DONE) return;
   int ready = -1;
@@ -384,83 +490,9 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
     if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
     __syncwarp();
   }
-  if (!only_begin && e.phase != PH_DONE) {
-    bool have = true;
-    if (P.source == RLM_SOURCE_GENERATOR) {
-      flow_next_warp(&e.flow, &msg, r12, lane);
-    } else {
-      const int pos = D.stream_off + tslot;
-      if (pos >= D.stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; have = false; }
-      else ((unsigned*)&msg)[lane] = __ldg((const unsigned*)(ptr.stream + ((size_t)pos * P.n_envs + env)) + lane);
-    }
-    if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);  // issued early, consumed after the book logic
-    __syncwarp();
-    const int phase = e.phase;
-    if (have && phase == PH_PREOPEN) {  // intraday.cpp:111-116
-      if (lane == 0) {
-        msg.n_tx = 0;
-        update_book_profiles(e, msg);
-        if (market_is_open(e)) e.phase = PH_WARMUP;
-      }
-    } else if (have) {
-      ticked = 1;
-      if (lane == 0 && phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
-      __syncwarp();
-      next_state_warp(e, msg, pushv, fills, lane);  // Intraday::NextState, ask side on lane 0, bid side on lane 1
-      __syncwarp();
-      if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
-      __syncwarp();
-      if (lane == 0) {
-        int r = -1;
-        e.tp_val = e.w_mean[W_TP];
-        if (phase == PH_WARMUP) {  // intraday.cpp:118-135
-          bool full = true;
-          for (int w = 0; w < 8; ++w) full = full && (e.w_count[w] == P.win_size[w]);
-          if (full) {
-            place_orders(e, 1, 1);
-            e.phase = PH_RUN;
-            e.ag.kind = 1;  // serial.cpp:24-25,55-60: the first from-state is the never-populated State
-            r = 1;
-          }
-        } else {
-          // tail of one iteration of performAction's do-while (base.cpp:292-305)
-          double mpm = m_midprice(e) - m_last_midprice(e);
-          e.pnl_step += (double)e.position * mpm;
-          e.momentum_pnl_step += (double)e.position * mpm;
-          e.agg_r += get_reward(e);
-          e.agg_pnl += e.pnl_step;
-          e.agg_mpm += mpm;
-          if (!(!is_terminal(e) && fabs(e.agg_mpm) < 1e-5)) {
-            e.pnl_step = e.agg_pnl;  // base.cpp:317-331
-            pushv[W_PNLUP] = fmax(0.0, e.pnl_step);
-            pushv[W_PNLDN] = fabs(fmin(0.0, e.pnl_step));
-            e.ep_reward += e.agg_r;
-            e.ep_bandh += e.agg_mpm;
-            r = 0;
-          }
-        }
-        *flag = r;
-      }
-      __syncwarp();
-      ready = *flag;
-      if (ready == 0) {
-        if (lane == W_PNLUP || lane == W_PNLDN) window_push(e, ring, lane, pushv[lane], oldv[lane]);
-        __syncwarp();
-        // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
-        if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
-        if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
-      } else if (ready == 1 && D.backtest) {
-        // Backtester::_step builds its state from the env before every action (serial.cpp:126), the first one included
-        if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
-      }
-    }
-  }
+  if (!only_begin && e.phase != PH_DONE) ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, lane, ticked);
   __syncwarp();
-  {
-    int4* dst = (int4*)g;
-    const int4* src = (const int4*)&e;
-    for (int i = lane; i < hdr_bytes / 16; i += 32) dst[i] = src[i];
-  }
+  envw_stage_out(g, &e, lane);
   if (lane == 0) {
     if (ready >= 0) ptr.ready[atomicAdd(&ptr.ready_count[tslot], 1)] = env;
     if (ticked) atomicAdd(&ptr.counters[0], 1ull);
@@ -492,6 +524,18 @@ __device__ __forceinline__ void emit_record(const DevPtrs& ptr, const EnvHdr* g,
 __device__ __noinline__ void emit_record_ool(const DevPtrs& ptr, const EnvHdr* g, int env, const AgentD& ag, const double* theta_a,
                                              const float* vars, int lane) {
   emit_record(ptr, g, env, ag, theta_a, vars, lane);
+}
+// the same for a record that is resident in the warp's shared memory (fused engine)
+__device__ __noinline__ void emit_record_res(const DevPtrs& ptr, const EnvHdr* e, int env, const AgentD& ag, const double* theta_a,
+                                             const float* vars, int lane) {
+  const int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
+  const float* te = ptr.trace_e + (size_t)env * P.trace_cap;
+  const unsigned long long h = trace_hash(tf, te, theta_a, ag.n_traces, lane);
+  if (lane == 0) {
+    const int c = ptr.record_count[env];
+    if (c < P.record_cap) fill_record(&ptr.records[(size_t)env * P.record_cap + c], *e, ag, h, vars);
+    ptr.record_count[env] = c + 1;
+  }
 }
 
 // Backtester::_step (serial.cpp:121-137) after a step ended (kind 0) or after Intraday::Initialise (kind 1):
@@ -607,6 +651,26 @@ __device__ __noinline__ void td_rho(AgentD& ag, const double* q_post_a, const do
   if (nQ - best < 1e-7) ag.rho += P.beta * (ag.last_reward - ag.rho + boot - nQ);
 }
 
+#ifdef RLM_TIMING  // debug build only (see the Makefile): per-CTA phase timeline of the learner kernel
+__device__ long long g_phase_clk[4096 * 16];
+__device__ unsigned g_phase_sm[4096];
+#define PH(i) do { if (tid == 0 && idx < 4096) { g_phase_clk[idx * 16 + (i)] = clock64(); if ((i) == 0) { unsigned s_; asm volatile("mov.u32 %0, %%smid;" : "=r"(s_)); g_phase_sm[idx] = s_; } } } while (0)
+extern "C" int rlm_debug_read_phases(long long* clk, unsigned* sm) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(clk, g_phase_clk, sizeof(long long) * 4096 * 16) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(sm, g_phase_sm, sizeof(unsigned) * 4096) != cudaSuccess) return -1;
+  long long tp[8];
+  if (cudaMemcpyFromSymbol(tp, g_tp_clk, sizeof(tp)) == cudaSuccess)
+    printf("slowest trace_pass so far: %lld cycles = set build %lld + decay loop %lld + set() %lld; n=%lld decay=%lld\n", tp[0], tp[1], tp[2], tp[3],
+           tp[4], tp[5]);
+  return 0;
+}
+#else
+#define PH(i) do { } while (0)
+#endif
+
+#include "rlm_learn.cuh"
+
 // The learner step of one ready env, by one warp.  `ag` / `scratch` are this warp's shared memory.
 // stage 0: the whole step (independent policies).  Shared policy (one theta per handle):
 // stage 1 = evaluate under theta_t and accumulate the update into dtheta; stage 2 (after
@@ -643,7 +707,7 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
   double* theta_b = ptr.theta_b ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
   unsigned* occ_w = ptr.occ + pol * (size_t)P.occ_words;
   // once a quarter of an env's table is nonzero the bitmap test costs more than it saves: gather directly
-  const unsigned* occ = (!P.shared_policy && (long long)ag.n_occ * 4 > P.memory_size) ? nullptr : occ_w;
+  const unsigned* occ = nullptr;  // (round 2: the occupancy bitmap is no longer consulted -- every gather goes to theta)
   unsigned long long bases[3];
   if (D.backtest) {
     const int kind = ag.kind;
@@ -655,21 +719,24 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
     }
   } else if (stage == 2) {
     if (ag.kind == 0) {
-      if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+      if (lane < RLM_N_STATE_MAX + 3) { ag.prev_vars[lane] = ag.from_vars[lane]; ag.from_vars[lane] = ag.to_vars[lane]; }
       __syncwarp();
       double qa, qb;
       eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, false, vbuf, lane, qa, qb, bases, false, idxc, occ);
       if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
       ag.from_base0[lane] = mod_m(bases[0]);
-      if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+      if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
       steps_done++;
     }
   } else if (ag.kind == 1) {
-    // end of warm-up: Q(null state, .) for the very first action selection
+    // end of warm-up: Q(first from-state, .) for the first action selection: the never-populated State in a Learner's
+    // first episode, the previous episode's stale State afterwards (serial.cpp:24-25,55,60)
     double qa, qb;
-    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, true, vbuf, lane, qa, qb, bases, false, idxc, occ);
+    const bool nullf = ag.null_from != 0;
+    eval_q(s_rnd, theta_a, theta_b, ag.from_vars, P.n_state_vars, nullf, vbuf, lane, qa, qb, bases, false, idxc, occ);
     if (lane < A) { ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
-    if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; ag.kind = 2; }
+    if (!nullf) ag.from_base0[lane] = mod_m(bases[0]);
+    if (lane == 0) { ag.need_begin = 1; ag.kind = 2; }
   } else {
     int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
     float* te = ptr.trace_e + (size_t)env * P.trace_cap;
@@ -734,9 +801,9 @@ __device__ __noinline__ void agent_process_env(const DevPtrs& ptr, const DynPara
     }
     if (stage == 0) {
       // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
-      if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+      if (lane < RLM_N_STATE_MAX + 3) { ag.prev_vars[lane] = ag.from_vars[lane]; ag.from_vars[lane] = ag.to_vars[lane]; }
       ag.from_base0[lane] = mod_m(bases[0]);
-      if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+      if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
       __syncwarp();
       {
         double qa, qb;
@@ -918,24 +985,6 @@ __device__ __noinline__ int a3_backtest_step(const DevPtrs& ptr, const EnvHdr* g
   return (int)steps_done;
 }
 
-#ifdef RLM_TIMING  // debug build only (make EXTRA=-DRLM_TIMING): per-CTA phase timeline of the learner kernel
-__device__ long long g_phase_clk[4096 * 16];
-__device__ unsigned g_phase_sm[4096];
-#define PH(i) do { if (tid == 0 && idx < 4096) { g_phase_clk[idx * 16 + (i)] = clock64(); if ((i) == 0) { unsigned s_; asm volatile("mov.u32 %0, %%smid;" : "=r"(s_)); g_phase_sm[idx] = s_; } } } while (0)
-extern "C" int rlm_debug_read_phases(long long* clk, unsigned* sm) {
-  cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(clk, g_phase_clk, sizeof(long long) * 4096 * 16) != cudaSuccess) return -1;
-  if (cudaMemcpyFromSymbol(sm, g_phase_sm, sizeof(unsigned) * 4096) != cudaSuccess) return -1;
-  long long tp[8];
-  if (cudaMemcpyFromSymbol(tp, g_tp_clk, sizeof(tp)) == cudaSuccess)
-    printf("slowest trace_pass so far: %lld cycles = set build %lld + decay loop %lld + set() %lld; n=%lld decay=%lld\n", tp[0], tp[1], tp[2], tp[3],
-           tp[4], tp[5]);
-  return 0;
-}
-#else
-#define PH(i) do { } while (0)
-#endif
-
 // EXTRAS = false: the Q-learning / SARSA / Double-Q training kernel; EXTRAS = true adds the R-learning agents' third
 // evaluation and the backtest step (separate instantiation so that they cost the training path no registers).
 template <bool EXTRAS>
@@ -985,8 +1034,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
 #define A3_OCC_READY() do { if (P.occ_smem_words) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncthreads(); } } while (0)
     // the bitmap test pays for itself as long as it filters enough gathers: against HBM-resident bitmaps up to a
     // quarter full, against the shared-memory copy (a test is one LDS) up to 15/16 full
-    const bool dense = !P.shared_policy && (P.occ_smem_words > 0 ? (long long)ag.n_occ * 16 > P.memory_size * 15
-                                                                  : (long long)ag.n_occ * 4 > P.memory_size);
+    const bool dense = true;  // round 2: the occupancy bitmap is no longer consulted (dense tables are the regime that counts)
     const bool occ_sm = !dense && P.occ_smem_words > 0;
     const unsigned* occ = dense ? nullptr : (occ_sm ? occ_s : occ_w);
     const int kind = ag.kind;
@@ -1003,21 +1051,23 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         if (warp == 0) {
           double qa, qb;
           if (lane < A) { a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
-          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          if (lane < RLM_N_STATE_MAX + 3) { ag.prev_vars[lane] = ag.from_vars[lane]; ag.from_vars[lane] = ag.to_vars[lane]; }
           ag.from_base0[lane] = mod_m(base);
-          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
           steps_done++;
         }
       }
     } else if (kind == 1) {  // end of warm-up: Q(null state, .)
-      a3_hash(rnd, ag.from_vars, P.n_state_vars, true, warp, lane, f);
+      const bool nullf = ag.null_from != 0;  // a Learner's first episode; afterwards the previous episode's stale State
+      base = a3_hash(rnd, ag.from_vars, P.n_state_vars, nullf, warp, lane, f);
       A3_OCC_READY();
       a3_gather(theta_a, theta_b, occ, occ_sm, f, warp, lane, V);
       __syncthreads();
       if (warp == 0) {
         double qa, qb;
         if (lane < A) { a3_sums(V, theta_b != nullptr, lane, qa, qb); ag.q_from[lane] = qa; ag.qb_from[lane] = qb; }
-        if (lane == 0) { ag.null_from = 1; ag.need_begin = 1; ag.kind = 2; }
+        if (!nullf) ag.from_base0[lane] = mod_m(base);
+        if (lane == 0) { ag.need_begin = 1; ag.kind = 2; }
       }
     } else if (kind == 0) {
       if (stage == 1) {  // shared policy: Q(from, .) under theta_t (agent.cpp:274,285 read theta at update time)
@@ -1068,18 +1118,18 @@ __global__ void __launch_bounds__(A3_WARPS * 32, 10) rlm_agent3_kernel(DevPtrs p
         PH(8);
         if (env < P.record_envs) emit_record(ptr, g, env, ag, theta_a, ag.to_vars, lane);
         if (!EXTRAS && stage == 0) {
-          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          if (lane < RLM_N_STATE_MAX + 3) { ag.prev_vars[lane] = ag.from_vars[lane]; ag.from_vars[lane] = ag.to_vars[lane]; }
           ag.from_base0[lane] = mod_m(base);
-          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
           steps_done++;
         }
       }
       if (EXTRAS) {
         if (P.algorithm >= RLM_ALGO_R_LEARN) a3_rho_step(ag, theta_a, theta_b, occ, occ_sm, V, q_pre_a, q_pre_b, dec, D, warp, lane);
         if (warp == 0 && stage == 0) {  // (after the other warps have read from_vars in a3_rho_step)
-          if (lane < RLM_N_STATE_MAX + 3) ag.from_vars[lane] = ag.to_vars[lane];
+          if (lane < RLM_N_STATE_MAX + 3) { ag.prev_vars[lane] = ag.from_vars[lane]; ag.from_vars[lane] = ag.to_vars[lane]; }
           ag.from_base0[lane] = mod_m(base);
-          if (lane == 0) { ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+          if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
           steps_done++;
         }
       }
@@ -1466,8 +1516,7 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
     rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
     return cudaGetLastError();
   }
-  const size_t per_warp = ((sizeof(EnvHdr) + 15) & ~(size_t)15) + 128 + 8 * 2 * RLM_NWIN + 128;
-  const size_t smem = ENVW_WARPS * per_warp;
+  const size_t smem = ENVW_WARPS * envw_warp_bytes();
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

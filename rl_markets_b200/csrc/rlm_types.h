@@ -65,7 +65,11 @@ struct alignas(16) AgentD {
   int ep_step, err;
   int n_occ;   // independent policies: bits set in this env's occupancy bitmap; > M/4 => treat theta as dense
   double rho;  // R-learning average reward (agent.h:131,145,157); lives as long as theta does
-  int pad;
+  // from-state of the last completed transition: Runner's two State objects survive RunEpisode (serial.h:17-23), so the
+  // next episode's first action is chosen from -- and its first transition starts at -- this state (serial.cpp:24-25,55,60)
+  float prev_vars[RLM_N_STATE_MAX + 3];
+  int prev_null;
+  int pad[3];
 };
 
 struct EnvHdr {
@@ -104,6 +108,7 @@ struct DevParams {
   unsigned long long m_magic;  // floor(2^64 / M)
   int m_pow2;
   int ra_m[RLM_MAX_ACTIONS];  // rndseq[(a + 449*4) & 2047] mod M: the action term of a group-0 tile hash
+  unsigned rg[3][RLM_MAX_ACTIONS];  // rndseq[(g*A + a + 449*(nf_g + 1)) & 2047]: the action term of group g's tile hash (tiles.cpp:65-68)
   float gl;  // (float)(gamma*lambda): Traces::decay(float rate)
   double gw[3], gamma, beta;
   float damping, pos_weight, trd_weight, pnl_weight;

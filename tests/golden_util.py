@@ -16,7 +16,12 @@ def _all_cases():
 
 def manifest():
     """Single-episode training cases."""
-    return [c for c in _all_cases() if not c.get("backtest")]
+    return [c for c in _all_cases() if not c.get("backtest") and not c.get("multi_episode")]
+
+
+def episode_manifest():
+    """N training episodes on one Intraday + one Learner-equivalent (main.cpp:45-60)."""
+    return [c for c in _all_cases() if c.get("multi_episode")]
 
 
 def backtest_manifest():

@@ -67,6 +67,7 @@ def lib():
         L.lobo_handle_terminal.argtypes = [C.c_void_p, C.c_int]
         L.lobo_go_greedy.argtypes = [C.c_void_p]
         L.lobo_reset.argtypes = [C.c_void_p]
+        L.lobo_reset_fresh_learner.argtypes = [C.c_void_p]
         L.lobo_set_backtest.argtypes = [C.c_void_p, C.c_int]
         L.lobo_new_env.argtypes = [C.c_void_p]
         L.lobo_rho.argtypes = [C.c_void_p]
@@ -160,7 +161,7 @@ def write_ref_yaml(path, ydict):
 
 
 def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=None, want_theta=False, t0_ms=None,
-            test=None):
+            test=None, episodes=1):
     """Run the UNMODIFIED reference (oracle/_ref/ref_driver) on the CSV rendering of the same flow.
     test = dict(flow_seed, env, ticks, t0_ms): also run main.cpp's evaluation phase (greedy agent, new env,
     Backtester) on a second stream; its records come back as "test_records"."""
@@ -178,6 +179,8 @@ def run_ref(ydict, flow_seed, env_index, n_ticks, dt_ms=250, max_steps=-1, algo=
                "--dump", dump, "--steps", str(max_steps)]
         if algo:
             cmd += ["--algo", algo]
+        if episodes != 1:  # one Intraday + one Learner-equivalent reused over N episodes (main.cpp:45-60)
+            cmd += ["--episodes", str(episodes)]
         if want_theta:
             cmd += ["--theta", thp]
         dump2 = os.path.join(d, "test_steps.bin")

@@ -23,6 +23,39 @@ def test_step_records_match_the_reference(rlm):
         recs, _keep = m.records(0)
         gold, _k2 = G.records(case["name"])
         assert len(recs) >= len(gold) > 100, (case["name"], len(recs))
+        # mm_exp calls exp()/pow() (base.cpp:216-221): glibc's in the reference, CUDA's here -- both within an ulp of the
+        # true value but not identical, so THIS case is held to the north star's 1e-5 relative bar on the fp64 fields that
+        # depend on the reward (observed ~1e-9) and bitwise on everything else (integer book state included)
+        tol = {"reward", "ep_reward", "delta", "trace_hash"} if case["yaml"]["reward"]["measure"] == "mm_exp" else set()
+        for i, g in enumerate(gold):
+            bad = abi.record_fields_equal(g, recs[i])
+            for f in [f for f in bad if f in tol and f != "trace_hash"]:
+                x, y = getattr(g, f), getattr(recs[i], f)
+                assert abs(x - y) <= 1e-5 * max(abs(x), abs(y)), (case["name"], i, f, x, y)
+            bad = [f for f in bad if f not in tol]
+            assert not bad, "%s step %d (reference, cuda): %r" % (case["name"], i, G.describe_diff(g, recs[i], bad))
+        m.close()
+
+
+def test_multi_episode_records_match_the_reference(rlm):
+    """N training episodes on one env + one Learner (main.cpp:45-60, serial.cpp:72-95) against the reference's own dump:
+    rlm_handle_terminal(episode) + rlm_reset carry the stale State of Runner into the next episode (serial.cpp:24-25,55,60)
+    and keep the window sums Base::Initialise does not clear (accumulators.cpp:60-64)."""
+    for case in G.episode_manifest():
+        cfg = G.case_config(case, n_envs=3, env_index0=case["env"])
+        cfg.flow.t0_ms = case["t0_ms"]
+        cfg.record_envs = 1
+        cfg.record_cap = case["n_records"] + 16
+        m = rlm.BatchedMarket(cfg)
+        for ep in range(case["episodes"]):
+            m.run_ticks(case["ticks"])  # more than the day holds: the env stops at the close
+            m.sync()
+            assert m.stats(0, 1)[0].terminal == 1
+            m.handle_terminal(ep)
+            m.reset()
+        recs, _keep = m.records(0)
+        gold, _k2 = G.records(case["name"])
+        assert len(recs) == len(gold) == case["n_records"], (case["name"], len(recs), len(gold))
         for i, g in enumerate(gold):
             bad = abi.record_fields_equal(g, recs[i])
             assert not bad, "%s step %d (reference, cuda): %r" % (case["name"], i, G.describe_diff(g, recs[i], bad))

@@ -126,6 +126,11 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
     ({"RLM_ENGINE": "p"}, "sarsa"),               # persistent queue engine
     ({"RLM_ENGINE": "f"}, "double_q_learn"),      # fused warp-per-env engine
     ({"RLM_ENGINE": "f"}, "r_learn"),
+    ({"RLM_ENGINE": "F"}, "q_learn"),             # fused persistent engine, round 2 (rlm_fused2_kernel)
+    ({"RLM_ENGINE": "F"}, "sarsa"),
+    ({"RLM_ENGINE": "F"}, "double_q_learn"),
+    ({"RLM_ENGINE": "s"}, "q_learn"),             # tick-synchronous engine (two launches per tick)
+    ({"RLM_ENGINE": "s", "RLM_AGENT_VARIANT": "3"}, "sarsa"),  # ... with the round-1 three-warp learner kernel
 ])
 def test_every_engine_variant_matches_oracle(rlm, oracle, monkeypatch, env_vars, algo):
     """The non-default kernels (selected by environment variables read in rlm_create) are held to the same bar."""

@@ -24,6 +24,32 @@ def test_golden_step_records_bitwise(oracle):
             assert not bad, "%s step %d: %r" % (case["name"], i, G.describe_diff(g, port["records"][i], bad))
 
 
+def test_golden_multi_episode_records_bitwise(oracle):
+    """N episodes on one Intraday + one Learner (main.cpp:45-60): HandleTerminal(episode), the same day again, Initialise;
+    the first transition of every later episode starts at the previous episode's stale State (serial.cpp:24-25,55,60)."""
+    L = oracle.lib()
+    for case in G.episode_manifest():
+        cfg = G.case_config(case)
+        cfg.flow.t0_ms = case["t0_ms"]
+        ticks = oracle.lib_generate(cfg, case["env"], case["ticks"])
+        h = L.lobo_create(C.byref(cfg), case["env"])
+        got = []
+        for ep in range(case["episodes"]):
+            recs = (abi.StepRecord * case["ticks"])()
+            used = C.c_int64()
+            n = L.lobo_run(h, ticks, case["ticks"], -1, recs, case["ticks"], C.byref(used))
+            assert n > 50 and L.lobo_is_terminal(h) == 1
+            got += [recs[i] for i in range(n)]
+            L.lobo_handle_terminal(h, ep)  # serial.cpp:79
+            L.lobo_reset(h)
+        gold, _k = G.records(case["name"])
+        assert len(got) == len(gold) == case["n_records"]
+        for i, g in enumerate(gold):
+            bad = abi.record_fields_equal(g, got[i])
+            assert not bad, "%s step %d: %r" % (case["name"], i, G.describe_diff(g, got[i], bad))
+        L.lobo_destroy(h)
+
+
 def test_golden_backtest_records_bitwise(oracle):
     """Train until the close, then main.cpp:216-241 (GoGreedy, a new Intraday, Backtester) -- vs the reference."""
     L = oracle.lib()

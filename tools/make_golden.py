@@ -41,6 +41,45 @@ CASES = [
 ]
 
 
+# SURVEY 8f rank 2, the rest: every reward measure (base.cpp:166-237), all 13 state variables (intraday.cpp:315-409),
+# the Random policy (policy.cpp:27-30), and the other two target-price / quote rules (base.cpp:101-112, intraday.cpp:64-82).
+# 150 records each keep the fixtures small.
+_ALL_VARS = ["pos", "spd", "mpm", "imb", "svl", "vol", "rsi", "vwap", "a_dist", "a_queue", "b_dist", "b_queue", "last_action"]
+F2_CASES = [
+    dict(name="rew_none", algo="q_learn", M=8192, flow_seed=31, env=10, ticks=1200, over={"reward.measure": "none"}),
+    dict(name="rew_pnl", algo="q_learn", M=8192, flow_seed=31, env=11, ticks=1200, over={"reward.measure": "pnl"}),
+    dict(name="rew_spread", algo="sarsa", M=8192, flow_seed=31, env=12, ticks=1200, over={"reward.measure": "spread"}),
+    dict(name="rew_normed", algo="q_learn", M=8192, flow_seed=31, env=13, ticks=1200,
+         over={"reward.measure": "normed", "reward.pnl_lookback": 12}),
+    dict(name="rew_lovol", algo="q_learn", M=8192, flow_seed=31, env=14, ticks=1200, over={"reward.measure": "lovol"}),
+    dict(name="rew_mm_linear", algo="q_learn", M=8192, flow_seed=31, env=15, ticks=1200,
+         over={"reward.measure": "mm_linear", "reward.pos_weight": 0.5, "reward.pnl_weight": 0.75}),
+    dict(name="rew_mm_exp", algo="q_learn", M=8192, flow_seed=31, env=16, ticks=1200,
+         over={"reward.measure": "mm_exp", "reward.pos_weight": 0.02, "reward.pnl_weight": 1.0}),
+    dict(name="rew_mm_div", algo="double_q_learn", M=8192, flow_seed=31, env=17, ticks=1200, over={"reward.measure": "mm_div"}),
+    dict(name="vars13", algo="q_learn", M=16384, flow_seed=33, env=18, ticks=1200,
+         over={"state.variables": _ALL_VARS, "state.lookback.rsi": 10, "state.lookback.vwap": 20}),
+    dict(name="vars13_sarsa_defaults", algo="sarsa", M=16384, flow_seed=33, env=19, ticks=1200,
+         over={"state.variables": list(reversed(_ALL_VARS))}),  # rsi / vwap lookbacks 0 -> windows of 1
+    dict(name="policy_random", algo="q_learn", M=8192, flow_seed=35, env=20, ticks=1200, over={"policy.type": "random"}),
+    dict(name="policy_greedy", algo="sarsa", M=8192, flow_seed=35, env=21, ticks=1200, over={"policy.type": "greedy"}),
+    dict(name="tp_microprice", algo="q_learn", M=8192, flow_seed=37, env=22, ticks=1200,
+         over={"market.target_price.type": "microprice", "market.target_price.lookback": 5}),  # -> tp::MidPrice (A1)
+    dict(name="tp_book", algo="q_learn", M=8192, flow_seed=37, env=23, ticks=1200, over={"market.target_price.type": "book"}),
+]
+N_F2_RECORDS = 150
+
+# N training episodes on ONE Intraday and ONE Learner-equivalent (main.cpp:45-60, serial.cpp:72-95): the day ends
+# `open_ticks` rows after the first one, HandleTerminal(episode), LoadData of the same day again, Initialise.
+EPISODE_CASES = [
+    dict(name="ep3_q_learn_m8192", algo="q_learn", M=8192, flow_seed=41, env=24, ticks=700, open_ticks=500, episodes=3,
+         over={"learning.omega": 0.9, "learning.alpha_start": 0.01, "policy.eps_T": 3}),
+    dict(name="ep3_double_q_m8192", algo="double_q_learn", M=8192, flow_seed=43, env=25, ticks=700, open_ticks=500, episodes=3,
+         over={"learning.omega": 0.8, "learning.alpha_start": 0.01, "policy.eps_T": 2}),
+    dict(name="ep2_sarsa_boltzmann_m8192", algo="sarsa", M=8192, flow_seed=45, env=26, ticks=700, open_ticks=500, episodes=2,
+         over={"policy.type": "boltzmann", "policy.tau_init": 0.05, "policy.tau_floor": 0.01, "policy.tau_T": 2}),
+]
+
 # train on one (short) synthetic day until the close, then main.cpp's evaluation phase (GoGreedy, a NEW Intraday,
 # Backtester::RunEpisode) on another one: steps_<name>.bin = training records, steps_<name>_test.bin = evaluation
 BACKTEST_CASES = [
@@ -77,6 +116,31 @@ def main():
                 f.write(bytes(r))
         manifest.append(dict(c, yaml=y, n_records=len(recs), summary=ref["summary"]))
         print(c["name"], len(recs), "records;", ref["summary"]["steps"], "reference steps")
+    for c in F2_CASES:
+        y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
+        y_run = json.loads(json.dumps(y))
+        y_run["debug"]["random_seed"] = y["debug"]["random_seed"] + c["env"]
+        ref = ol.run_ref(y_run, c["flow_seed"], c["env"], c["ticks"])
+        recs = ref["records"][:N_F2_RECORDS]
+        assert len(recs) == N_F2_RECORDS, (c["name"], len(recs))
+        with open(os.path.join(GOLD, "steps_%s.bin" % c["name"]), "wb") as f:
+            for r in recs:
+                f.write(bytes(r))
+        manifest.append(dict(c, yaml=y, n_records=len(recs), summary=ref["summary"]))
+        print(c["name"], len(recs), "records;", ref["summary"]["steps"], "reference steps")
+    for c in EPISODE_CASES:
+        y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
+        y_run = json.loads(json.dumps(y))
+        y_run["debug"]["random_seed"] = y["debug"]["random_seed"] + c["env"]
+        cfg = config.from_dict(y)
+        t0 = day_t0(cfg, c["open_ticks"])
+        ref = ol.run_ref(y_run, c["flow_seed"], c["env"], c["ticks"], t0_ms=t0, episodes=c["episodes"])
+        assert ref["summary"]["terminal"] == 1
+        with open(os.path.join(GOLD, "steps_%s.bin" % c["name"]), "wb") as f:
+            for r in ref["records"]:
+                f.write(bytes(r))
+        manifest.append(dict(c, yaml=y, multi_episode=True, t0_ms=t0, n_records=len(ref["records"]), summary=ref["summary"]))
+        print(c["name"], len(ref["records"]), "records over", c["episodes"], "episodes")
     for c in BACKTEST_CASES:
         y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
         seed = y["debug"]["random_seed"] + c["env"]
