@@ -1,14 +1,16 @@
 #!/usr/bin/env python3
 """bench.py -- env steps/sec of the batched LOB + tile-coded TD hot path on B200.
 
-One bench "step" = one launch of the fused tick kernel: TICKS_PER_LAUNCH market ticks for every
-one of the B environments (about TICKS/K learner steps per env).  The metric is BASELINE.json's:
-env steps/sec, one env step = one experiment::serial::Learner::_step (src/experiment/serial.cpp:53-70).
+One bench "step" = `--ticks` market ticks for every one of the B environments of the workload (about TICKS/3.4 learner
+steps per env).  The metric is BASELINE.json's: env steps/sec, one env step = one experiment::serial::Learner::_step
+(src/experiment/serial.cpp:53-70).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs B] [--algo ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C1..C4] [--no-extras]
 
-N > 1 is launched by torchrun (one rank per GPU); envs are sharded by rank, independent policies
-need no data-path collective ("scaling": "weak").
+N > 1 is launched by torchrun (one rank per GPU); envs are sharded by rank, independent policies need no data-path
+collective ("scaling": "weak").  The headline is C1 (BASELINE.json configs[1]) per GPU; the line also carries, under
+"extra", short measurements of the other configs: C2 (the largest single-GPU config) at N = 1, C3 (shared policy, one
+NCCL all-reduce per tick) and C4 at N > 1.
 """
 import argparse
 import ctypes as C
@@ -23,17 +25,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TICKS_PER_LAUNCH = 64
+TICKS_PER_STEP = 1024  # device-resident leg: 20 driver steps = 20 480 ticks, a timed region of about a second at C1
+E2E_TICKS = 64         # end-to-end leg: one upload chunk (32 MB of messages at C1)
 WORKLOADS = {
     # BASELINE.json configs[1]: 4096 parallel LOBs, Q-learning tile coding, synthetic Poisson flow, 1xB200
-    "C1": dict(envs=4096, algo="q_learn", memory_size=65536, shared=False),
+    "C1": dict(envs=4096, algo="q_learn", memory_size=65536, shared=False, pretrain=108000, ticks=TICKS_PER_STEP),
     # configs[2]: 65536 LOBs, SARSA(lambda) with eligibility traces, 1xB200
-    "C2": dict(envs=65536, algo="sarsa", memory_size=16384, shared=False),
+    "C2": dict(envs=65536, algo="sarsa", memory_size=16384, shared=False, pretrain=20000, ticks=128),
     # configs[3]: 262144 LOBs over 8 GPUs (32768 per GPU), shared policy, per-tick NCCL all-reduce of dtheta
-    "C3": dict(envs=32768, algo="q_learn", memory_size=1 << 22, shared=True),
+    "C3": dict(envs=32768, algo="q_learn", memory_size=1 << 22, shared=True, pretrain=4000, ticks=64),
     # configs[4]: 1M LOBs over 8 GPUs (131072 per GPU), independent policies, no collective
-    "C4": dict(envs=131072, algo="q_learn", memory_size=4096, shared=False),
+    "C4": dict(envs=131072, algo="q_learn", memory_size=4096, shared=False, pretrain=12000, ticks=64),
 }
+# tools/ubench/gather.cu on this pool's B200 (profiles/r2_ubench_gather.txt): independent 8-byte loads at random offsets
+# inside a per-warp 512 KB window of a multi-GB array complete at 53.6 G loads/s whatever the parallelism (1.7 TB/s of
+# 32-byte sectors = 26 % of the copy bandwidth): the DRAM ceiling of a tile-coded evaluation whose table does not fit
+# on chip.  A coalesced 32 KB window per step streams at 6.6-7.0 TB/s instead.
+DRAM_RANDOM_SECTORS_PER_S = 53.6e9
+
+
+def workload_string(name, B, algo, M):
+    """Identical in the `ours` and `reference` arms (the driver compares it)."""
+    return "%s: %d parallel LOBs per GPU, %s + tile coding (32 tilings, memory_size %d per env), synthetic Poisson order flow" % (
+        name, B, algo, M)
 
 
 def algorithmic_bytes_per_step(k_ticks, z_traces, double_q=False):
@@ -49,6 +63,19 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    """Threads this process may actually use: the affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
 
 
 class ClockSampler(threading.Thread):
@@ -82,7 +109,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_cfg(workload, n_envs, env_index0, source, args):
-    from rl_markets_b200 import abi, config
+    from rl_markets_b200 import config
     w = WORKLOADS[workload]
     y = config.example_dict(**{"learning.memory_size": args.memory_size or w["memory_size"],
                                "learning.algorithm": args.algo or w["algo"]})
@@ -92,269 +119,281 @@ def make_cfg(workload, n_envs, env_index0, source, args):
     return y, cfg
 
 
-def run_ours(args):
+class Ctx:
+    pass
+
+
+def _setup():
     import torch
-    from rl_markets_b200 import abi, lib
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = Ctx()
+    ctx.torch = torch
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
+    torch.cuda.set_device(ctx.local)
+    ctx.dist = None
+    if ctx.world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w = WORKLOADS[args.workload]
-    B = args.envs or w["envs"]
-    y, cfg = make_cfg(args.workload, B, rank * B, abi.SOURCE_GENERATOR, args)
-    cfg.device = local
-    m = lib.BatchedMarket(cfg)
-    stream = torch.cuda.Stream()
-    m.set_stream(stream.cuda_stream)
-    ticks = args.ticks
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local))
+        ctx.dist = dist
+    ctx.stream = torch.cuda.Stream()
+    return ctx
+
+
+def _barrier(ctx):
+    ctx.torch.cuda.synchronize()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    ctx.torch.cuda.synchronize()
+
+
+def _allreduce(ctx, vals, op):
+    if ctx.dist is None:
+        return [float(v) for v in vals]
+    t = ctx.torch.tensor([float(v) for v in vals], device="cuda", dtype=ctx.torch.float64)
+    ctx.dist.all_reduce(t, op=getattr(ctx.dist.ReduceOp, op))
+    return [float(x) for x in t]
+
+
+def measure(ctx, name, args, steps, warmup, headline):
+    """Device-resident measurement of one workload; returns (dict for rank 0, market, cfg)."""
+    torch = ctx.torch
+    from rl_markets_b200 import abi, lib, parallel
+    w = WORKLOADS[name]
+    B = (args.envs if (headline and args.envs) else w["envs"])
+    M = (args.memory_size if (headline and args.memory_size) else w["memory_size"])
+    algo = (args.algo if (headline and args.algo) else w["algo"])
+    ticks = (args.ticks if (headline and args.ticks) else w["ticks"])
+    pretrain = (args.pretrain_ticks if (headline and args.pretrain_ticks >= 0) else w["pretrain"])
     shared = bool(w.get("shared"))
-    from rl_markets_b200 import parallel
-    dist_mod = None
-    if world > 1:
-        import torch.distributed as dist_mod  # noqa: F811
+    sub = argparse.Namespace(**vars(args))
+    sub.memory_size, sub.algo = M, algo
+    y, cfg = make_cfg(name, B, ctx.rank * B, abi.SOURCE_GENERATOR, sub)
+    cfg.device = ctx.local
+    m = lib.BatchedMarket(cfg)
+    m.set_stream(ctx.stream.cuda_stream)
 
-    def run_chunk():
-        if shared and world > 1:
-            with torch.cuda.stream(stream):
-                parallel.run_shared_policy(m, ticks, dist_mod)
+    def run_chunk(n):
+        if shared and ctx.world > 1:
+            with torch.cuda.stream(ctx.stream):
+                parallel.run_shared_policy(m, n, ctx.dist)
         else:
-            m.run_ticks(ticks)
+            m.run_ticks(n)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- cold start (informational): the first steps of training from all-zero weight tables.  They are cheap -- the
-    # learner kernel skips gathers of weights that were never written -- and NOT representative of a training run,
-    # which keeps theta across ~1000 episodes (src/main.cpp:47-80): reported next to the headline, never as it.
+    # ---- cold start (informational): the first steps of training from all-zero weight tables
     cold = None
-    if args.pretrain_ticks > 0:
-        for _ in range(3):
-            run_chunk()
+    if headline and pretrain > 0:
+        run_chunk(256)
         m.sync()
         cc_a = m.counters()
-        n_cold = min(args.steps, 20)
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(stream):
-            ev_a.record(stream)
-            for _ in range(n_cold):
-                run_chunk()
-            ev_b.record(stream)
-        barrier()
+        _barrier(ctx)
+        with torch.cuda.stream(ctx.stream):
+            ev_a.record(ctx.stream)
+            run_chunk(ticks)
+            ev_b.record(ctx.stream)
+        _barrier(ctx)
         m.sync()
-        cold = {"ms": ev_a.elapsed_time(ev_b), "steps": m.counters().steps - cc_a.steps, "n": n_cold}
-        # ---- pre-training (untimed): one reference trading day (LSE, 250 ms rows: 108 000 ticks) so that the timed
-        # region sees weight tables in their long-run state
-        left = args.pretrain_ticks
-        while left > 0:
-            if shared and world > 1:
-                with torch.cuda.stream(stream):
-                    parallel.run_shared_policy(m, min(left, 256), dist_mod)
-            else:
-                m.run_ticks(min(left, 256))
-            left -= 256
-        m.sync()
-    occ_start = None
+        cold = {"ms": ev_a.elapsed_time(ev_b), "steps": m.counters().steps - cc_a.steps}
+    # ---- pre-training (untimed) so that the timed region sees weight tables in their long-run state: the reference keeps
+    # theta across ~1000 episodes (src/main.cpp:47-80).  C1: one LSE trading day of the reference's 250 ms rows.
+    left = pretrain
+    while left > 0:
+        run_chunk(min(left, 512))
+        left -= 512
+    m.sync()
+    occ = None
     if not shared:
         o = m.occupancy()
-        occ_start = sum(o) / len(o) / float(args.memory_size or w["memory_size"])
-
-    # ---- device-resident run (inputs = generator state, theta, traces: all in HBM)
-    for _ in range(max(args.warmup, 3)):
-        run_chunk()
+        occ = sum(o) / len(o) / float(M)
+    for _ in range(max(warmup, 3)):
+        run_chunk(ticks)
     m.sync()
     c0 = m.counters()
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with torch.cuda.stream(stream):
-        evs[0].record(stream)
-        for i in range(args.steps):
-            run_chunk()
-            evs[i + 1].record(stream)
-    barrier()
-    sampler.stop_flag = True
+    sampler = ClockSampler(ctx.local) if headline else None
+    if sampler:
+        sampler.start()
+    _barrier(ctx)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    with torch.cuda.stream(ctx.stream):
+        evs[0].record(ctx.stream)
+        for i in range(steps):
+            run_chunk(ticks)
+            evs[i + 1].record(ctx.stream)
+    _barrier(ctx)
+    if sampler:
+        sampler.stop_flag = True
     m.sync()
     c1 = m.counters()
     total_ms = evs[0].elapsed_time(evs[-1])
-    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    if rank == 0 and os.environ.get("RLM_BENCH_TRACE"):  # how the step time moves as the weight tables fill up
-        sys.stderr.write("ms per bench step: " + " ".join("%.2f" % x for x in per_launch_ms[::max(1, args.steps // 40)]) + "\n")
-    steps_done = c1.steps - c0.steps
-    ticks_done = c1.ticks - c0.ticks
-    z_sum = c1.sum_traces - c0.sum_traces
-    launches_timed = c1.kernel_launches - c0.kernel_launches
-
-    # ---- per-kernel durations (CUDA events around every launch, on the launching stream): a separate pass,
-    # because the events serialise host launch and device execution; not used for `value`
-    kt = None
-    if not shared:
-        m.set_profiling(True)
-        cp0 = m.counters()
-        for _ in range(min(args.steps, 5)):
-            m.run_ticks(ticks)
-        m.sync()
-        cp1 = m.counters()
-        kt = m.kernel_times()
-        kt["steps"] = cp1.steps - cp0.steps
-        kt["ticks"] = cp1.ticks - cp0.ticks
-        kt["sum_traces"] = cp1.sum_traces - cp0.sum_traces
-        m.set_profiling(False)
-
-    # ---- end to end through the C ABI with HOST buffers: every launch uploads its tick messages from
-    # pinned host memory (rlm_load_ticks) and reads the per-env rewards back (rlm_get_reward)
-    e2e = None
-    if not args.no_e2e and not shared:
-        y2, cfg2 = make_cfg(args.workload, B, rank * B, abi.SOURCE_STREAM, args)
-        cfg2.device = local
-        m2 = lib.BatchedMarket(cfg2)
-        m2.set_stream(stream.cuda_stream)
-        m2.copy_theta_from(m)  # same long-run weight tables as the device-resident leg (a new data day, trained agent)
-        n_warm = max(args.warmup, 3)
-        e2e_steps_n = min(args.steps, 20)  # 32 MB of pinned host memory per step at C1: the e2e leg times at most 20 of them
-        nbytes = ticks * B * C.sizeof(abi.TickMsg)
-        gen_ticks = ticks * (n_warm + e2e_steps_n)
-        # synthetic messages for all envs, generated once on the host cores and staged in pinned host memory
-        # BEFORE the timed region (one pinned chunk per bench step; nothing host-side is excluded from the timing)
-        import numpy as np
-        per_env = [lib.flow_generate(cfg2.flow, rank * B + b, 0, gen_ticks) for b in range(min(B, args.e2e_distinct))]
-        env_np = [np.frombuffer(pe, dtype=np.uint8).reshape(gen_ticks, 128) for pe in per_env]
-        rew = (C.c_double * B)()
-
-        def staged(chunk):
-            host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            host_np = host.numpy().view(np.uint8).reshape(ticks, B, 128)
-            for b in range(B):  # envs beyond e2e_distinct replay the stream of env (b mod distinct)
-                host_np[:, b, :] = env_np[b % len(env_np)][chunk * ticks:(chunk + 1) * ticks]
-            return host
-
-        for ch in range(n_warm):
-            host = staged(ch)
-            m2.load_ticks(host.data_ptr(), ticks)
-            m2.run_ticks(ticks)
-            m2.sync()
-        chunks = [staged(n_warm + i) for i in range(e2e_steps_n)]
-        cc0 = m2.counters()
-        barrier()
-        t0 = time.perf_counter()
-        # rlm_load_ticks double-buffers on a copy stream: the upload of step i+1 is issued before the result of
-        # step i is read, so it overlaps step i's kernels; all K uploads and K read-backs are inside the region
-        m2.load_ticks(chunks[0].data_ptr(), ticks)
-        for i in range(e2e_steps_n):
-            m2.run_ticks(ticks)
-            if i + 1 < e2e_steps_n:
-                m2.load_ticks(chunks[i + 1].data_ptr(), ticks)   # H2D inside the timed region
-            lib.check(m2.L.rlm_get_reward(m2.h, rew))  # D2H inside the timed region (syncs)
-        barrier()
-        wall = time.perf_counter() - t0
-        cc1 = m2.counters()
-        e2e_steps = cc1.steps - cc0.steps
-        e2e = {"steps": e2e_steps, "seconds": wall, "h2d": nbytes, "d2h": B * 8, "n": e2e_steps_n}
-        m2.close()
-
-    # ---- aggregate over ranks: max time, sum steps
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([total_ms, (e2e or {}).get("seconds", 0.0)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([steps_done, ticks_done, z_sum, (e2e or {}).get("steps", 0)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        total_ms = float(t[0]); steps_all, ticks_all, z_all = float(s[0]), float(s[1]), float(s[2])
-        if e2e:
-            e2e["seconds"] = float(t[1]); e2e["steps"] = float(s[3])
-    else:
-        steps_all, ticks_all, z_all = float(steps_done), float(ticks_done), float(z_sum)
-
+    steps_done, ticks_done, z_sum = c1.steps - c0.steps, c1.ticks - c0.ticks, c1.sum_traces - c0.sum_traces
+    launches = c1.kernel_launches - c0.kernel_launches
+    total_ms = _allreduce(ctx, [total_ms], "MAX")[0]
+    steps_all, ticks_all, z_all = _allreduce(ctx, [steps_done, ticks_done, z_sum], "SUM")
     if cold is not None:
-        if world > 1:
-            import torch.distributed as dist
-            tc = torch.tensor([cold["ms"]], device="cuda", dtype=torch.float64)
-            sc = torch.tensor([float(cold["steps"])], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-            dist.all_reduce(sc, op=dist.ReduceOp.SUM)
-            cold["ms"], cold["steps"] = float(tc[0]), float(sc[0])
-    if rank == 0:
+        cold["ms"] = _allreduce(ctx, [cold["ms"]], "MAX")[0]
+        cold["steps"] = _allreduce(ctx, [cold["steps"]], "SUM")[0]
+    res = None
+    if ctx.rank == 0:
         k_bar = ticks_all / max(steps_all, 1.0)
         z_bar = z_all / max(steps_all, 1.0)
-        is_dq = (args.algo or w["algo"]) == "double_q_learn"
+        is_dq = algo == "double_q_learn"
         b_step = algorithmic_bytes_per_step(k_bar, z_bar, is_dq)
         value = steps_all / (total_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = rlm_agent3_kernel (one launch per market tick); its algorithmic bytes are the agent
-        # share of B_step: theta gathers + trace list (13824 + 28 Z per env step), SURVEY.md section 8d
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_summary.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("agent_kernel_dram_bytes_per_launch")
-        except Exception:
-            pass
-        if kt and kt["agent_launches"]:
-            avg_launch_ms = kt["agent_ms"] / kt["agent_launches"]
-            launch_steps = kt["steps"] / kt["agent_launches"]
-            z_k = kt["sum_traces"] / max(kt["steps"], 1)
-            b_agent = (27648.0 if is_dq else 13824.0) + 28.0 * z_k
-            achieved = launch_steps * b_agent / (avg_launch_ms * 1e-3) / 1e9
-            env_avg_ms = kt["env_ms"] / max(kt["env_launches"], 1)
-        else:
-            avg_launch_ms = total_ms / max(launches_timed, 1)
-            launch_steps = steps_done / max(launches_timed, 1)
-            b_agent = b_step
-            achieved = steps_done * b_step / (total_ms * 1e-3) / 1e9
-            env_avg_ms = None
-        line = {
-            "metric": "env steps/sec (batched LOBs)", "value": value, "unit": "env_steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %d parallel LOBs per GPU, %s + tile coding (32 tilings, memory_size %d per env), "
-                                   "synthetic Poisson order flow (in-kernel generator), %d ticks per launch"
-                                   % (args.workload, B, args.algo or w["algo"], args.memory_size or w["memory_size"], ticks),
-                       "envs_per_gpu": B, "ticks_per_bench_step": ticks, "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar,
-                       "policy": "shared theta, one SUM all-reduce of dtheta per tick" if shared else "independent theta per env, no collective",
-                       "l2": ("working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * (args.memory_size or w["memory_size"]) * 8 / 1e9))
-                             if not shared else ("shared theta %.0f MB (L2-resident) + %.1f GB of env records, traces and generator state" % ((args.memory_size or w["memory_size"]) * 8 / 1e6, B * 8.0e3 / 1e9)),
-                       "ticks_per_s": ticks_all / (total_ms * 1e-3),
-                       "pretrain_ticks": args.pretrain_ticks,
-                       "theta_occupancy_at_start": occ_start,
-                       "state": ("timed after %d ticks of training per env (one LSE trading day of the reference's 250 ms rows): "
-                                 "long-run weight tables" % args.pretrain_ticks) if args.pretrain_ticks > 0
-                                else "cold start: all-zero weight tables (gathers of never-written weights are skipped)"},
-            "gpu_launches": int(launches_timed),
-            "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "rlm_agent3_kernel (learner step, one launch per market tick)",
-                         "algorithmic_bytes_per_env_step_agent_kernel": b_agent,
-                         "algorithmic_bytes_per_env_step_whole_path": b_step,
-                         "whole_path_achieved_GBps": steps_all * b_step / (total_ms * 1e-3) / 1e9 / max(world, 1),
-                         "env_steps_per_launch": launch_steps, "avg_launch_ms": avg_launch_ms,
-                         "env_kernel_avg_launch_ms": env_avg_ms,
-                         "timing": "CUDA events around every kernel launch on the launching stream, separate pass"},
+        per_gpu = value / max(ctx.world, 1)
+        achieved = per_gpu * b_step / 1e9
+        engine = os.environ.get("RLM_ENGINE", "s")[:1]
+        fused = engine == "F" and not shared
+        # DRAM sectors one env step touches at random when the table does not fit on chip: 864 gathers + Z re-reads of
+        # updated weights that miss + 2 Z for the read-modify-write of theta (28 Z algorithmic bytes are trace-list traffic)
+        sectors = (1728.0 if is_dq else 864.0) + 2.0 * z_bar
+        res = {
+            "workload": workload_string(name, B, algo, M), "value": value, "unit": "env_steps/s",
+            "ms_per_step": total_ms / steps, "steps": steps, "ticks_per_bench_step": ticks, "envs_per_gpu": B,
+            "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar, "ticks_per_s": ticks_all / (total_ms * 1e-3),
+            "pretrain_ticks": pretrain, "theta_nonzero_fraction_at_start": occ, "gpu_launches": int(launches),
+            "policy": "shared theta, one SUM all-reduce of dtheta per tick" if shared else "independent theta per env, no collective",
+            "l2": ("working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * M * 8 / 1e9)) if not shared
+                  else ("shared theta %.0f MB (L2-resident) + %.1f GB of env records, traces and generator state" % (M * 8 / 1e6, B * 8.0e3 / 1e9)),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_nominal_8TBs": achieved / 8000.0, "traffic": None, "peak_source": peak_src,
+                "kernel": ("rlm_fused2_kernel (market ticks + learner steps of all envs, one launch per bench step)" if fused else
+                           "whole tick (env tick kernel + learner kernel, two launches per market tick)"),
+                "algorithmic_bytes_per_env_step": b_step,
+                "env_steps_per_launch": (steps_all / max(ctx.world, 1)) / max(launches, 1),
+                "avg_launch_ms": total_ms / max(launches, 1) if fused else None,
+                "timing": "CUDA events on the launching stream around the timed region (max over ranks); per GPU",
+                "dram_random_access_ceiling": {
+                    "sectors_per_s": DRAM_RANDOM_SECTORS_PER_S, "random_sectors_per_env_step": sectors,
+                    "env_steps_per_s": DRAM_RANDOM_SECTORS_PER_S / sectors, "frac_of_ceiling": per_gpu / (DRAM_RANDOM_SECTORS_PER_S / sectors),
+                    "source": "tools/ubench/gather.cu, profiles/r2_ubench_gather.txt: random 8-byte gathers from a table larger than L2"
+                              + ("" if M > 8192 else " (tables of <= 64 KB are staged whole by cp.async.bulk instead: this ceiling does not apply)")},
+            },
         }
         if cold is not None:
-            line["cold_start"] = {"value": cold["steps"] / (cold["ms"] * 1e-3), "unit": "env_steps/s", "steps": cold["n"],
-                                  "note": "first bench steps of training from all-zero weight tables; informational, not the headline"}
+            res["cold_start"] = {"value": cold["steps"] / (cold["ms"] * 1e-3), "unit": "env_steps/s",
+                                 "note": "first bench step of training from all-zero weight tables; informational"}
+        if sampler:
+            res["clocks"] = sampler.summary()
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_summary.json")) as f:
+                prof = json.load(f).get(name)
+            if prof:
+                res["roofline"]["traffic"] = prof["dram_bytes_per_env_step"] * res["roofline"]["env_steps_per_launch"]
+                res["roofline"]["traffic_source"] = prof.get("source")
+        except Exception:
+            pass
+    return res, m, cfg, (B, M, algo, ticks)
+
+
+def e2e_leg(ctx, m, name, args, shape):
+    """The same metric through the C ABI with HOST buffers: every step uploads its tick messages from pinned host memory
+    (rlm_load_ticks) and reads the per-env rewards back (rlm_get_reward).  All B envs get their own stream."""
+    torch = ctx.torch
+    import numpy as np
+    from rl_markets_b200 import abi, lib
+    B, M, algo, _ticks = shape
+    ticks = E2E_TICKS
+    sub = argparse.Namespace(**vars(args))
+    sub.memory_size, sub.algo = M, algo
+    y2, cfg2 = make_cfg(name, B, ctx.rank * B, abi.SOURCE_STREAM, sub)
+    cfg2.device = ctx.local
+    m2 = lib.BatchedMarket(cfg2)
+    m2.set_stream(ctx.stream.cuda_stream)
+    m2.copy_theta_from(m)  # same long-run weight tables as the device-resident leg (a new data day, trained agent)
+    n_warm, n_steps = 3, max(args.e2e_steps, 1)
+    nbytes = ticks * B * C.sizeof(abi.TickMsg)
+    gen_ticks = ticks * (n_warm + n_steps)
+    # synthetic messages of every env, generated on the host cores and staged in pinned host memory BEFORE the timed
+    # region (one pinned chunk per step); nothing host-side is excluded from the timing
+    distinct = min(B, args.e2e_distinct) if args.e2e_distinct > 0 else B
+    chunks = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(n_warm + n_steps)]
+    views = [c.numpy().view(np.uint8).reshape(ticks, B, 128) for c in chunks]
+    for b in range(distinct):
+        pe = np.frombuffer(lib.flow_generate(cfg2.flow, ctx.rank * B + b, 0, gen_ticks), dtype=np.uint8).reshape(gen_ticks, 128)
+        for k, v in enumerate(views):
+            v[:, b, :] = pe[k * ticks:(k + 1) * ticks]
+    for b in range(distinct, B):  # (only with --e2e-distinct: the remaining envs replay stream b mod distinct)
+        for v in views:
+            v[:, b, :] = v[:, b % distinct, :]
+    rew = (C.c_double * B)()
+    for ch in range(n_warm):
+        m2.load_ticks(chunks[ch].data_ptr(), ticks)
+        m2.run_ticks(ticks)
+        m2.sync()
+    cc0 = m2.counters()
+    _barrier(ctx)
+    t0 = time.perf_counter()
+    # rlm_load_ticks double-buffers on a copy stream: the upload of step i+1 is issued before the result of step i is
+    # read, so it overlaps step i's kernels; all uploads and all read-backs are inside the region
+    m2.load_ticks(chunks[n_warm].data_ptr(), ticks)
+    for i in range(n_steps):
+        m2.run_ticks(ticks)
+        if i + 1 < n_steps:
+            m2.load_ticks(chunks[n_warm + i + 1].data_ptr(), ticks)  # H2D inside the timed region
+        lib.check(m2.L.rlm_get_reward(m2.h, rew))                    # D2H inside the timed region (syncs)
+    _barrier(ctx)
+    wall = time.perf_counter() - t0
+    cc1 = m2.counters()
+    m2.close()
+    secs = _allreduce(ctx, [wall], "MAX")[0]
+    st = _allreduce(ctx, [cc1.steps - cc0.steps], "SUM")[0]
+    return {"value": st / secs, "unit": "env_steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": B * 8,
+            "steps": n_steps, "ticks_per_step": ticks, "distinct_streams": distinct,
+            "note": "STREAM source: rlm_load_ticks from pinned host memory (double-buffered upload) + rlm_run_ticks + rlm_get_reward per step"}
+
+
+def run_ours(args):
+    ctx = _setup()
+    res, m, cfg, shape = measure(ctx, args.workload, args, args.steps, args.warmup, headline=True)
+    e2e = None
+    if not args.no_e2e and not WORKLOADS[args.workload].get("shared"):
+        e2e = e2e_leg(ctx, m, args.workload, args, shape)
+    m.close()
+    extras = {}
+    if not args.no_extras:
+        names = ["C2"] if ctx.world == 1 else ["C3", "C4"]
+        for nm in names:
+            if nm == args.workload:
+                continue
+            try:
+                r, mx, _c, _s = measure(ctx, nm, args, steps=max(3, min(args.steps, 5)), warmup=3, headline=False)
+                mx.close()
+                if r is not None:
+                    extras[nm] = r
+            except Exception as ex:  # an extra must never cost the headline
+                if ctx.rank == 0:
+                    extras[nm] = {"error": str(ex)[:300]}
+    if ctx.rank == 0:
+        line = {
+            "metric": "env steps/sec (batched LOBs)", "value": res["value"], "unit": "env_steps/s", "n_gpus": ctx.world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": res["workload"], "envs_per_gpu": res["envs_per_gpu"], "ticks_per_bench_step": res["ticks_per_bench_step"],
+                       "mean_ticks_per_step": res["mean_ticks_per_step"], "mean_nonzero_traces": res["mean_nonzero_traces"],
+                       "policy": res["policy"], "l2": res["l2"], "ticks_per_s": res["ticks_per_s"],
+                       "flow": "in-kernel generator (device-resident leg); host-generated streams of every env (e2e leg)",
+                       "engine": {"F": "fused persistent kernel (one launch per bench step)", "s": "tick-synchronous (two launches per market tick)"}.get(
+                           os.environ.get("RLM_ENGINE", "s")[:1], os.environ.get("RLM_ENGINE", "")),
+                       "pretrain_ticks": res["pretrain_ticks"], "theta_nonzero_fraction_at_start": res["theta_nonzero_fraction_at_start"],
+                       "state": "timed after %d ticks of training per env: long-run weight tables" % res["pretrain_ticks"]},
+            "gpu_launches": res["gpu_launches"], "clocks": res.get("clocks"), "roofline": res["roofline"],
+        }
+        if "cold_start" in res:
+            line["cold_start"] = res["cold_start"]
         if e2e:
-            line["e2e"] = {"value": e2e["steps"] / e2e["seconds"], "unit": "env_steps/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "steps": e2e["n"],
-                           "note": "STREAM source: rlm_load_ticks from pinned host memory (double-buffered upload) + rlm_run_ticks + rlm_get_reward per step"}
-        if world == 1 and not args.no_cpu_baseline:
+            line["e2e"] = e2e
+        if extras:
+            line["extra"] = extras
+        if ctx.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_reference(args, n_procs=1, ticks=args.cpu_ticks)
         print(json.dumps(line))
-    m.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -376,7 +415,6 @@ def cpu_baseline_reference(args, n_procs, ticks):
     y = config.example_dict(**{"learning.memory_size": args.memory_size or w["memory_size"], "learning.algorithm": algo})
     if not os.path.exists(drv):
         # fall back to the CPU restatement ("port"), threads = n_procs
-        from rl_markets_b200 import abi
         cfg = config.from_dict(y, n_envs=n_procs, flow_seed=2024, dt_ms=1)
         L = oracle_lib.lib()
         tt, secs = C.c_int64(0), C.c_double(0)
@@ -434,10 +472,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_procs = os.cpu_count() or 1
+    n_procs = host_threads()
     drv, flow = _ref_paths()
     n_runs = max(args.warmup, 0) + args.steps
-    # one bench step = every host thread runs one single-env reference process over `ticks` ticks of the workload;
+    # one bench step = every usable host thread runs one single-env reference process over `ticks` ticks of the workload;
     # the sample is sized so that the whole --steps/--warmup run stays within a few minutes (~1e5 ticks/s per process)
     ticks = min(args.ref_ticks, max(10000, int(6e6 / max(n_runs, 1))))
     vals = []
@@ -465,9 +503,9 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "%s: %s + tile coding (memory_size %d per env), synthetic Poisson order flow; reference arm = "
-                                   "%d independent single-threaded reference processes on the host cores"
-                                   % (args.workload, args.algo or w["algo"], args.memory_size or w["memory_size"], n_procs)},
+            "config": {"workload": workload_string(args.workload, args.envs or w["envs"], args.algo or w["algo"], args.memory_size or w["memory_size"]),
+                       "reference_arm": "%d independent single-threaded reference processes (one per usable host thread: affinity mask "
+                                        "capped by the cgroup quota), each running ONE env of the workload" % n_procs},
             "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": n_procs, "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -476,18 +514,20 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--algo", default="")
     ap.add_argument("--memory-size", dest="memory_size", type=int, default=0)
-    ap.add_argument("--ticks", type=int, default=TICKS_PER_LAUNCH)
-    ap.add_argument("--pretrain-ticks", dest="pretrain_ticks", type=int, default=108000,
-                    help="untimed training before the timed region (default: one LSE day of 250 ms rows); 0 = cold start")
+    ap.add_argument("--ticks", type=int, default=0, help="market ticks per bench step (default: per workload, 1024 for C1)")
+    ap.add_argument("--pretrain-ticks", dest="pretrain_ticks", type=int, default=-1,
+                    help="untimed training before the timed region (default: per workload; C1 = one LSE day of 250 ms rows); 0 = cold start")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-distinct", type=int, default=64, help="distinct host-generated streams replayed across envs in the e2e leg")
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=20)
+    ap.add_argument("--e2e-distinct", type=int, default=0, help="0 = every env gets its own host-generated stream")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-ticks", type=int, default=400000)
     ap.add_argument("--ref-ticks", type=int, default=100000)

@@ -106,6 +106,13 @@ __device__ __forceinline__ int mod_m(unsigned long long sum) {  // (int)(sum % m
   return (int)r;
 }
 
+// (int) floor(float) as x86-64 evaluates it (cvttss2si): NaN and out-of-range values give INT_MIN ("integer
+// indefinite"), where CUDA's cvt would give 0 / saturate.  A NaN state variable is reachable: vwap over an empty volume
+// window is 0/0 (intraday.cpp:356-362) and tiles.cpp:56 quantises it like any other value.
+__device__ __forceinline__ int f2i_x86(float v) {
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return (int)0x80000000;
+  return (int)v;
+}
 // coordinate of tiling j for quantised value q at dimension i (tiles.cpp:56-63): base = j*(1+2i)
 __device__ __forceinline__ int tile_coord(int q, int i, int j) {
   int base = j * (1 + 2 * i);
@@ -122,7 +129,7 @@ __device__ __noinline__ unsigned long long tile_base_sum(const unsigned* rnd, co
   for (int i = 0; i < RLM_N_STATE_MAX; ++i) {
     v[i] = 0u;
     if (i < nf) {
-      int q = (int)floorf(vars[i] * (float)RLM_N_TILINGS);
+      int q = f2i_x86(floorf(vars[i] * (float)RLM_N_TILINGS));
       int c = tile_coord(q, i, j);
       v[i] = __ldg(rnd + ((c + 449 * i) & 2047));
     }
@@ -134,6 +141,44 @@ __device__ __noinline__ unsigned long long tile_base_sum(const unsigned* rnd, co
 }
 __device__ __forceinline__ int tile_index(const unsigned* rnd, unsigned long long base, int nf, int h1) {
   return mod_m(base + __ldg(rnd + ((h1 + 449 * (nf + 1)) & 2047)));
+}
+
+// ---- tile hashing of one state.  sums[g] = lane's partial hash sum of group g (everything but the action term);
+// tile (group g, tiling `lane`, action a) = (sums[g] + rg[g][a]) mod M.  The sums are what stays live across the step
+// (6 registers); the 27 indices are re-derived where they are needed (2 instructions each for a power-of-two M).
+struct LnSums { unsigned long long s[3]; bool null_state; };
+__device__ __forceinline__ LnSums ln_hash(const unsigned* __restrict__ rnd, const float* vars, bool null_state, int lane) {
+  const int n = P.n_state_vars;
+  LnSums out;
+  out.null_state = null_state;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const float* gv = (g == 1) ? vars + 3 : vars;
+    const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
+    const int NF_MAX = (g == 0) ? 3 : ((g == 1) ? RLM_N_STATE_MAX - 3 : RLM_N_STATE_MAX);
+    unsigned v[RLM_N_STATE_MAX];
+#pragma unroll
+    for (int i = 0; i < NF_MAX; ++i) {
+      v[i] = 0u;
+      if (i < nf) {
+        const int q = f2i_x86(floorf(gv[i] * (float)RLM_N_TILINGS));
+        v[i] = __ldg(rnd + ((tile_coord(q, i, lane) + 449 * i) & 2047));
+      }
+    }
+    unsigned long long sum = __ldg(rnd + ((lane + 449 * nf) & 2047));
+#pragma unroll
+    for (int i = 0; i < NF_MAX; ++i) sum += v[i];
+    out.s[g] = null_state ? 0ull : sum;
+  }
+  return out;
+}
+template <bool POW2>
+__device__ __forceinline__ int ln_tile(const LnSums& h, int k) {  // k = g*9 + a
+  if (POW2) {  // (sum + r) mod 2^k only needs the low words; null state: sums are 0 and so is every index (hash_UNH is skipped)
+    const unsigned lo = (unsigned)h.s[k / RLM_MAX_ACTIONS] + P.rg[k / RLM_MAX_ACTIONS][k % RLM_MAX_ACTIONS];
+    return h.null_state ? 0 : (int)(lo & (unsigned)(P.memory_size - 1));
+  }
+  return h.null_state ? 0 : mod_m(h.s[k / RLM_MAX_ACTIONS] + P.rg[k / RLM_MAX_ACTIONS][k % RLM_MAX_ACTIONS]);
 }
 
 // Exact-order Q(s,a) for all actions (agent.cpp:117-135): lanes gather theta for their tiling,

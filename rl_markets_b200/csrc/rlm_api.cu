@@ -29,6 +29,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
                                        std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
+#define RLM_MAX_SUB 8
 struct rlm_handle_s {
   rlm_config cfg;
   DevParams hp;
@@ -64,6 +65,11 @@ struct rlm_handle_s {
   void* d_gather = nullptr; void* h_gather = nullptr; size_t gather_cap = 0;  // rlm_get_reward/actions/state staging
   long long launches = 0;
   double alpha = 0, eps = 0, tau = 1.0;
+  // tick-synchronous engine: the batch is cut into n_sub sub-batches, each ticking on its own stream, so that the
+  // DRAM-bound gather burst of one sub-batch's learner kernel overlaps the issue-bound scalar tick kernel of another
+  int n_sub = 1;
+  cudaStream_t sub_stream[RLM_MAX_SUB] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[RLM_MAX_SUB] = {};
 };
 
 static const rlm_handle_s* g_params_owner = nullptr;
@@ -217,16 +223,20 @@ static int derive(rlm_handle_s* h) {
   return RLM_OK;
 }
 
-static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tslot, int stage) {
+static cudaError_t launch_agent_on(rlm_handle_s* h, const DevPtrs& ptr, const DynParams& d, int tslot, int stage, cudaStream_t st) {
+  const int n = d.n_sub > 0 ? d.n_sub : h->cfg.n_envs;  // worst case: every env of the (sub-)batch is ready
   // Q-learning / SARSA / Double-Q training: the one-warp-per-env learner (rlm_learn.cuh).  The R-learning agents' third
   // evaluation and the backtest step stay on the three-warp kernel's EXTRAS instantiation.
   if (h->agent_variant == 4 && !d.backtest && h->cfg.algorithm < RLM_ALGO_R_LEARN)
-    return rlm_launch_learn(h->ptr, d, h->cfg.n_envs, h->hp.is_double, tslot, h->n_sms, stage, h->stream);
+    return rlm_launch_learn(ptr, d, n, h->hp.is_double, tslot, h->n_sms, stage, st);
   if (h->agent_variant >= 3) {
     const int full = (d.backtest || h->cfg.algorithm >= RLM_ALGO_R_LEARN) ? 1 : 0;
-    return rlm_launch_agent3(h->ptr, d, h->cfg.n_envs, h->hp.is_double, h->hp.occ_smem_words, tslot, h->n_sms, stage, full, h->stream);
+    return rlm_launch_agent3(ptr, d, n, h->hp.is_double, h->hp.occ_smem_words, tslot, h->n_sms, stage, full, st);
   }
-  return rlm_launch_agent(h->ptr, d, h->cfg.n_envs, h->hp.scratch_bytes, tslot, h->n_sms, stage, h->stream);
+  return rlm_launch_agent(ptr, d, n, h->hp.scratch_bytes, tslot, h->n_sms, stage, st);
+}
+static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tslot, int stage) {
+  return launch_agent_on(h, h->ptr, d, tslot, stage, h->stream);
 }
 
 static int upload_params(rlm_handle_s* h) {
@@ -299,10 +309,24 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   h->eps = (double)cfg->eps_init;
   h->tau = (double)cfg->tau_init;  // Boltzmann ctor (policy.cpp:85-96, main.cpp:157-162)
   memset(&h->dyn, 0, sizeof(h->dyn));
+#ifdef RLM_TIMING
+  if (const char* s = getenv("RLM_DEBUG_FLAGS")) h->dyn.debug_flags = atoi(s);
+#endif
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaMalloc(&h->ptr.ready, (size_t)cfg->n_envs * 4));
+  CK(cudaMalloc(&h->ptr.hsum, (size_t)cfg->n_envs * 3 * 32 * 8));
   h->ready_cap = 256;
-  CK(cudaMalloc(&h->ptr.ready_count, (size_t)h->ready_cap * 4));
+  CK(cudaMalloc(&h->ptr.ready_count, (size_t)RLM_MAX_SUB * h->ready_cap * 4));
+  // sub-batches of the tick-synchronous engine (see rlm_handle_s::n_sub): 4 streams from 2048 envs up
+  h->n_sub = (cfg->n_envs >= 2048 && !cfg->shared_policy) ? 4 : 1;
+  if (const char* s = getenv("RLM_SUBBATCHES")) { const int v = atoi(s); if (v >= 1 && v <= RLM_MAX_SUB) h->n_sub = cfg->shared_policy ? 1 : v; }
+  if (h->n_sub > 1) {
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int s = 0; s < h->n_sub; ++s) {
+      CK(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_join[s], cudaEventDisableTiming));
+    }
+  }
   {
     int dev_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -356,9 +380,14 @@ int rlm_destroy(rlm_handle h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
-  cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count); cudaFree(h->ptr.occ);
+  cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count); cudaFree(h->ptr.occ); cudaFree(h->ptr.hsum);
   cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
   for (auto e : h->ev) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int s = 0; s < RLM_MAX_SUB; ++s) {
+    if (h->sub_stream[s]) { cudaStreamSynchronize(h->sub_stream[s]); cudaStreamDestroy(h->sub_stream[s]); }
+    if (h->ev_join[s]) cudaEventDestroy(h->ev_join[s]);
+  }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (g_params_owner == h) g_params_owner = nullptr;
   delete h;
@@ -506,23 +535,46 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
   }
   // two kernels per tick (env tick, then the learner step of the envs whose midprice moved), then one
   // trailing env pass that only runs the pending action selections, so that the observable state
-  // after the call is "every env sits inside performAction's loop"
+  // after the call is "every env sits inside performAction's loop".  With n_sub > 1 every sub-batch does this on its own
+  // stream (forked from and joined to the handle's stream), its own ready list and its own ready counters.
+  const int S = (h->profile || h->n_sub < 1) ? 1 : h->n_sub;
+  const int B = h->cfg.n_envs;
+  int sub0[RLM_MAX_SUB + 1];
+  {
+    const int per = (((B + S - 1) / S) + 31) & ~31;  // whole warps of the thread-per-env kernel, whole CTAs of the warp-per-env one
+    for (int s = 0; s <= S; ++s) sub0[s] = std::min(B, s * per);
+  }
+  if (S > 1) {
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    for (int s = 0; s < S; ++s) CK(cudaStreamWaitEvent(h->sub_stream[s], h->ev_fork, 0));
+  }
   int done = 0;
   while (done < n_ticks) {
     const int chunk = std::min(n_ticks - done, h->ready_cap);
-    CK(cudaMemsetAsync(h->ptr.ready_count, 0, (size_t)chunk * 4, h->stream));
     if (h->profile) {
       while ((int)h->ev.size() < 3 * chunk) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev.push_back(e); }
     }
+    for (int s = 0; s < S; ++s)
+      CK(cudaMemsetAsync(h->ptr.ready_count + (size_t)s * h->ready_cap, 0, (size_t)chunk * 4, S > 1 ? h->sub_stream[s] : h->stream));
     for (int t = 0; t < chunk; ++t) {
-      DynParams dt = d;
-      dt.stream_off = d.stream_off + done;
-      if (h->profile) CK(cudaEventRecord(h->ev[3 * t], h->stream));
-      CK(rlm_launch_env(h->ptr, dt, h->cfg.n_envs, t, 0, h->env_variant, h->stream));
-      if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 1], h->stream));
-      CK(launch_agent_any(h, dt, t, 0));
-      if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 2], h->stream));
-      h->launches += 2;
+      for (int s = 0; s < S; ++s) {
+        if (sub0[s + 1] <= sub0[s]) continue;
+        cudaStream_t st = S > 1 ? h->sub_stream[s] : h->stream;
+        DynParams dt = d;
+        dt.stream_off = d.stream_off + done;
+        dt.env0 = sub0[s];
+        dt.n_sub = sub0[s + 1] - sub0[s];
+        dt.sub_idx = s;
+        DevPtrs ps = h->ptr;
+        ps.ready = h->ptr.ready + sub0[s];
+        ps.ready_count = h->ptr.ready_count + (size_t)s * h->ready_cap;
+        if (h->profile) CK(cudaEventRecord(h->ev[3 * t], st));
+        CK(rlm_launch_env(ps, dt, B, t, 0, h->env_variant, st));
+        if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 1], st));
+        CK(launch_agent_on(h, ps, dt, t, 0, st));
+        if (h->profile) CK(cudaEventRecord(h->ev[3 * t + 2], st));
+        h->launches += 2;
+      }
     }
     if (h->profile) {
       CK(cudaStreamSynchronize(h->stream));
@@ -536,8 +588,19 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
     }
     done += chunk;
   }
-  CK(rlm_launch_env(h->ptr, d, h->cfg.n_envs, 0, 1, h->env_variant, h->stream));
-  h->launches++;
+  for (int s = 0; s < S; ++s) {
+    if (sub0[s + 1] <= sub0[s]) continue;
+    cudaStream_t st = S > 1 ? h->sub_stream[s] : h->stream;
+    DynParams dt = d;
+    dt.env0 = sub0[s];
+    dt.n_sub = sub0[s + 1] - sub0[s];
+    CK(rlm_launch_env(h->ptr, dt, B, 0, 1, h->env_variant, st));
+    h->launches++;
+    if (S > 1) {
+      CK(cudaEventRecord(h->ev_join[s], st));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join[s], 0));
+    }
+  }
   return RLM_OK;
 }
 

@@ -494,17 +494,24 @@ __device__ __noinline__ void next_state_warp(EnvHdr& e, const rlm_tick_msg& m, d
   }
 }
 
+// ulb() of include/utilities/maths.h:4-8 = std::max(std::min(val, ub), lb): a NaN `val` comes back as NaN (both
+// comparisons are false), whereas fmin/fmax would drop it -- the vwap variable with an empty volume window is 0/0
+__device__ __forceinline__ double ulb_ref(double val, double lb, double ub) {
+  const double m = (ub < val) ? ub : val;
+  return (m < lb) ? lb : m;
+}
+
 // Intraday::getVariable (intraday.cpp:315-409)
 __device__ __noinline__ double get_variable(EnvHdr& e, const double* ring, int v) {
   switch (v) {
     case RLM_VAR_POS: return (double)e.position / (double)P.order_size;
     case RLM_VAR_SPD: {
       double d = (double)(to_ticks(e.side[0].px[0], &e.err) - to_ticks(e.side[1].px[0], &e.err));
-      return fmax(fmin(d, 20.0), 0.0);
+      return ulb_ref(d, 0.0, 20.0);
     }
     case RLM_VAR_MPM: {
       double d = (double)(to_ticks(win_front(e, ring, W_MID), &e.err) - to_ticks(win_back(e, ring, W_MID), &e.err));
-      return fmax(fmin(d, 10.0), -10.0);
+      return ulb_ref(d, -10.0, 10.0);
     }
     case RLM_VAR_IMB: {
       double v_a = (double)e.side[0].total_vol, v_b = (double)e.side[1].total_vol;
@@ -514,14 +521,14 @@ __device__ __noinline__ double get_variable(EnvHdr& e, const double* ring, int v
       double q_a = e.w_sum[W_ASKTX], q_b = e.w_sum[W_BIDTX];
       return ((q_a + q_b) > 0 ? 5.0 * (q_b - q_a) / (q_a + q_b) : 0.0);
     }
-    case RLM_VAR_VOL: return fmax(fmin(5.0 * win_std(e, W_VLT), 10.0), 0.0);
+    case RLM_VAR_VOL: return ulb_ref(5.0 * win_std(e, W_VLT), 0.0, 10.0);
     case RLM_VAR_RSI: {
       double u = e.ewma_up, d = e.ewma_dn;
       return (u + d) != 0.0 ? 5.0 * (u - d) / (u + d) : 0.0;
     }
     case RLM_VAR_VWAP: {
       double d = e.w_sum[W_VNUM] / e.w_sum[W_VDEN];
-      return fmax(fmin(d / e.w_mean[W_SPREAD], 10.0), -10.0);
+      return ulb_ref(d / e.w_mean[W_SPREAD], -10.0, 10.0);
     }
     case RLM_VAR_A_DIST:
       if (e.side[0].ord.live) return ((double)to_ticks(e.side[0].ord.price, &e.err) - (double)to_ticks(e.side[0].px[0], &e.err));

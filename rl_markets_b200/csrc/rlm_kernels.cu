@@ -25,6 +25,7 @@
 #include "rlm_agent.cuh"
 #include <cstdio>
 #include "rlm_kernels.h"
+#define RLM_SMEM_CARVEOUT 88  // percent of the 228 KB L1/shared array configured as shared memory, for every per-tick kernel
 
 // ---- one-warp-per-env learner (rlm_agent_kernel, fused and persistent engines): per warp [AgentD][scratch]
 // (the 8 KB hashing table is read through L1)
@@ -57,6 +58,26 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+#ifdef RLM_TIMING  // launch timeline: [tick slot][sub-batch][kernel: 0 env, 1 learner][0 first CTA start, 1 last CTA end], ns (globaltimer)
+__device__ unsigned long long g_klog[256][8][2][2];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define KLOG_BEGIN(kind) do { if (threadIdx.x == 0 && tslot < 256) atomicMin(&g_klog[tslot][D.sub_idx & 7][kind][0], gtime()); } while (0)
+#define KLOG_END(kind) do { if (threadIdx.x == 0 && tslot < 256) atomicMax(&g_klog[tslot][D.sub_idx & 7][kind][1], gtime()); } while (0)
+extern "C" int rlm_debug_klog(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out && cudaMemcpyFromSymbol(out, g_klog, sizeof(g_klog)) != cudaSuccess) return -1;
+  if (reset) {
+    static unsigned long long init[256][8][2][2];
+    for (auto& a : init) for (auto& b : a) for (auto& c : b) { c[0] = ~0ull; c[1] = 0ull; }
+    if (cudaMemcpyToSymbol(g_klog, init, sizeof(init)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#else
+#define KLOG_BEGIN(kind) do { } while (0)
+#define KLOG_END(kind) do { } while (0)
+#endif
 
 cudaError_t rlm_upload_params(const DevParams* p) { return cudaMemcpyToSymbol(P, p, sizeof(DevParams)); }
 
@@ -281,16 +302,17 @@ __device__ __noinline__ int env_tick(EnvHdr& e, double* ring, const rlm_tick_msg
   for (int i = 0; i < P.n_state_vars; ++i) e.ag.to_vars[i] = (float)get_variable(e, ring, P.state_vars[i]);
   e.ag.last_reward = get_reward(e);
   e.ag.kind = 0;
+  e.ag.hs_valid = 0;  // (one thread per env: the learner kernel hashes the to-state itself)
   return 0;
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams D, int tslot, int only_begin) {
-  const int b = blockIdx.x * THREADS + threadIdx.x;
+  const int b = D.env0 + blockIdx.x * THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int ready = -1;
   unsigned ticked = 0, errs = 0;
-  if (b < P.n_envs) {
+  if (b < (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) {
     EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
     const int ph = g->phase;
     const int nb = g->ag.need_begin;
@@ -459,6 +481,30 @@ __device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const D
       // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
       if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
       if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
+      if (!D.backtest && !P.shared_policy && P.algorithm < RLM_ALGO_R_LEARN) {
+        // The learner kernel's first act is 864 gathers from this env's weight table; they are DRAM misses, and an SM
+        // can only keep a few hundred of them in flight.  Hash the to-state here -- 31 lanes of this warp idle anyway --
+        // hand the sums over, and ask L2 for the 864 sectors now (prefetches carry no data back, so they do not queue
+        // behind the SM's miss tracking): they arrive under the tail of this kernel and the launch gap.
+        __syncwarp();
+        const LnSums h = ln_hash(rlm_rndseq_table, e.ag.to_vars, false, lane);
+        unsigned long long* hs = ptr.hsum + (size_t)env * 96;
+        hs[lane] = h.s[0]; hs[32 + lane] = h.s[1]; hs[64 + lane] = h.s[2];
+        const double* th_a = ptr.theta + (size_t)env * (size_t)P.memory_size;
+        const double* th_b = ptr.theta_b ? ptr.theta_b + (size_t)env * (size_t)P.memory_size : nullptr;
+#pragma unroll 1
+        for (int g = 0; g < 3; ++g) {
+#pragma unroll
+          for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
+            if (a < P.n_actions) {
+              const int f = mod_m(h.s[g] + P.rg[g][a]);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(th_a + f));
+              if (th_b) asm volatile("prefetch.global.L2 [%0];" ::"l"(th_b + f));
+            }
+          }
+        }
+        if (lane == 0) e.ag.hs_valid = 1;
+      }
     } else if (ready == 1 && D.backtest) {
       // Backtester::_step builds its state from the env before every action (serial.cpp:126), the first one included
       if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
@@ -472,8 +518,9 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   PDL_PROLOGUE();
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int env = blockIdx.x * ENVW_WARPS + warp;
-  if (env >= P.n_envs) return;
+  const int env = D.env0 + blockIdx.x * ENVW_WARPS + warp;
+  if (!only_begin) KLOG_BEGIN(0);
+  if (env >= (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) return;
   const EnvWarp w = envw_carve(smem + (size_t)warp * envw_warp_bytes());
   EnvHdr& e = *w.e;
   EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
@@ -493,6 +540,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   if (!only_begin && e.phase != PH_DONE) ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, lane, ticked);
   __syncwarp();
   envw_stage_out(g, &e, lane);
+  if (!only_begin) KLOG_END(0);
   if (lane == 0) {
     if (ready >= 0) ptr.ready[atomicAdd(&ptr.ready_count[tslot], 1)] = env;
     if (ticked) atomicAdd(&ptr.counters[0], 1ull);
@@ -1511,16 +1559,24 @@ int rlm_run_max_resident_ctas(int scratch_bytes, int n_sms) {
 
 // ---------------------------------------------------------------------------------------------
 cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, int only_begin, int variant, cudaStream_t st) {
+  if (D.n_sub > 0) n_envs = D.n_sub;  // one sub-batch
   if (variant == 1) {  // one thread per env (SIMT over envs)
     const int T = 32;
+    static bool attr1 = false;
+    if (!attr1) { cudaFuncSetAttribute(rlm_env_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT); attr1 = true; }
     rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
     return cudaGetLastError();
   }
   const size_t smem = ENVW_WARPS * envw_warp_bytes();
   static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  if (!attr) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    // the same L1/shared split as the learner kernel: CTAs of the two kernels (different sub-batches, different streams)
+    // can then share an SM instead of waiting for it to drain and be reconfigured
+    cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
     attr = true;
   }
   return launch_pdl(rlm_env_kernel_w, (n_envs + ENVW_WARPS - 1) / ENVW_WARPS, ENVW_WARPS * 32, smem, st, ptr, D, tslot, only_begin);

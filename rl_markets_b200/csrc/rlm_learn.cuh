@@ -13,13 +13,13 @@
 //   * argmax with rand() tie-breaks runs warp-wide (prefix maximum by shuffles); the serial scan is only taken
 //     when two values tie with the running maximum, which is when the reference draws rand();
 //   * the trace pass is the fused decay / clear / set / theta-update sweep of round 1 (one probe of the
-//     tile -> last-writer table per entry, RED.ADD.F64 at L2), the second evaluation re-reads only the tiles the
-//     update touched (Bloom filter);
+//     tile -> last-writer table per entry, RED.ADD.F64 at L2); the second evaluation does not read anything back: it
+//     adds this step's updates (kept in a shared-memory table) to the weights the first evaluation gathered;
 //   * no occupancy bitmap: tables are dense after the first thousands of steps, which is the regime that counts.
 // ~2000 warp-instructions per step instead of ~7700, no __syncthreads, no spills at 128 registers.
 #pragma once
 
-#define LN_WARPS 4
+#define LN_WARPS 3
 #ifdef RLM_TIMING
 #define LPH(i) do { if (lane == 0 && tp_idx < 4096) g_phase_clk[tp_idx * 16 + (i)] = clock64(); } while (0)
 #else
@@ -29,51 +29,17 @@
 #define LN_AG_BYTES 704
 
 __host__ __device__ inline size_t ln_v_bytes(int is_double) { return (size_t)(is_double ? 2 : 1) * RLM_MAX_ACTIONS * LN_VROW * 8; }
-// learner scratch of one step: [V][tile table 4096][bloom 512][q_pre 2*9 doubles][dec 6 doubles]
+// feature -> eligibility of every weight this step's update moved (open addressing): the second evaluation of the step
+// adds the update to the weights it already holds instead of reading them back from L2 behind the reductions
+#define UT_SLOTS 1024
+#define UT_MAX_ENTRIES 512
+// learner scratch of one step: [V][tile table 4096][update table 8192][q_pre 2*9 doubles][dec 6 doubles]
 __host__ __device__ inline size_t ln_scratch_bytes(int is_double) {
-  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + BLOOM_WORDS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
+  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
 }
 // per-warp shared memory of rlm_learn_kernel: [AgentD 704][scratch]
 __host__ __device__ inline size_t ln_warp_bytes(int is_double) { return (size_t)LN_AG_BYTES + ln_scratch_bytes(is_double); }
 static_assert(sizeof(AgentD) <= LN_AG_BYTES, "agent block outgrew its shared-memory slot");
-
-// ---- tile hashing of one state.  sums[g] = lane's partial hash sum of group g (everything but the action term);
-// tile (group g, tiling `lane`, action a) = (sums[g] + rg[g][a]) mod M.  The sums are what stays live across the step
-// (6 registers); the 27 indices are re-derived where they are needed (2 instructions each for a power-of-two M).
-struct LnSums { unsigned long long s[3]; bool null_state; };
-__device__ __forceinline__ LnSums ln_hash(const unsigned* __restrict__ rnd, const float* vars, bool null_state, int lane) {
-  const int n = P.n_state_vars;
-  LnSums out;
-  out.null_state = null_state;
-#pragma unroll
-  for (int g = 0; g < 3; ++g) {
-    const float* gv = (g == 1) ? vars + 3 : vars;
-    const int nf = (g == 0) ? 3 : ((g == 1) ? n - 3 : n);
-    const int NF_MAX = (g == 0) ? 3 : ((g == 1) ? RLM_N_STATE_MAX - 3 : RLM_N_STATE_MAX);
-    unsigned v[RLM_N_STATE_MAX];
-#pragma unroll
-    for (int i = 0; i < NF_MAX; ++i) {
-      v[i] = 0u;
-      if (i < nf) {
-        const int q = (int)floorf(gv[i] * (float)RLM_N_TILINGS);
-        v[i] = __ldg(rnd + ((tile_coord(q, i, lane) + 449 * i) & 2047));
-      }
-    }
-    unsigned long long sum = __ldg(rnd + ((lane + 449 * nf) & 2047));
-#pragma unroll
-    for (int i = 0; i < NF_MAX; ++i) sum += v[i];
-    out.s[g] = null_state ? 0ull : sum;
-  }
-  return out;
-}
-template <bool POW2>
-__device__ __forceinline__ int ln_tile(const LnSums& h, int k) {  // k = g*9 + a
-  if (POW2) {  // (sum + r) mod 2^k only needs the low words; null state: sums are 0 and so is every index (hash_UNH is skipped)
-    const unsigned lo = (unsigned)h.s[k / RLM_MAX_ACTIONS] + P.rg[k / RLM_MAX_ACTIONS][k % RLM_MAX_ACTIONS];
-    return h.null_state ? 0 : (int)(lo & (unsigned)(P.memory_size - 1));
-  }
-  return h.null_state ? 0 : mod_m(h.s[k / RLM_MAX_ACTIONS] + P.rg[k / RLM_MAX_ACTIONS][k % RLM_MAX_ACTIONS]);
-}
 
 // ---- gathers K0 .. K0+N-1 (k = g*9 + a) of one table in flight together; raw weights -> V[a][g*32 + lane]
 template <int K0, int N>
@@ -114,24 +80,37 @@ __device__ __forceinline__ void ln_gather(const double* __restrict__ th_a, const
   }
 }
 
-// second evaluation of a step: only tiles whose weight this step's update touched are read again
-__device__ __forceinline__ void ln_patch(const double* __restrict__ th_a, const double* __restrict__ th_b, const unsigned* bloom, const LnSums& h,
-                                         int lane, double* V) {
+// second evaluation of a step (same state, theta after this env's own update): theta_new[f] = theta_old[f] + update[f],
+// the one IEEE addition the L2 reduction performs, on the weight the first evaluation gathered -- no read-back
+__device__ __forceinline__ unsigned ut_hash(int f) { return ((unsigned)f * 2654435761u) >> 22; }  // 10 bits
+__device__ __forceinline__ void ut_clear(int* ut, int lane) {
+  int4* k4 = (int4*)ut;
+#pragma unroll
+  for (int i = 0; i < UT_SLOTS / 4 / 32; ++i) k4[lane + 32 * i] = make_int4(HS_EMPTY, HS_EMPTY, HS_EMPTY, HS_EMPTY);
+}
+__device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every f is inserted once per step
+  unsigned slot = ut_hash(f);
+  while (atomicCAS(&ut[slot], HS_EMPTY, f) != HS_EMPTY) slot = (slot + 1) & (UT_SLOTS - 1);
+  ((float*)(ut + UT_SLOTS))[slot] = ev;
+}
+__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
   const int A = P.n_actions;
   const bool pow2 = P.m_pow2 != 0;
 #pragma unroll 1
-  for (int g = 0; g < 3; ++g) {  // (rolled over the groups: this runs once per step and is mostly misses)
+  for (int g = 0; g < 3; ++g) {
 #pragma unroll
     for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
-      const int k = g * RLM_MAX_ACTIONS + a;
       const unsigned long long sum = h.s[g] + P.rg[g][a];
       const int f = h.null_state ? 0 : (pow2 ? (int)((unsigned)sum & (unsigned)(P.memory_size - 1)) : mod_m(sum));
-      if (a < A && bloom_test(bloom, f)) {
-        const int at = a * LN_VROW + g * 32 + lane;
-        V[at] = __ldcg(th_a + f);
-        if (th_b) V[RLM_MAX_ACTIONS * LN_VROW + at] = __ldcg(th_b + f);
+      if (a < A) {
+        unsigned slot = ut_hash(f);
+        int k = ut[slot];
+        while (k != HS_EMPTY && k != f) { slot = (slot + 1) & (UT_SLOTS - 1); k = ut[slot]; }
+        if (k == f) {
+          const int at = a * LN_VROW + g * 32 + lane;
+          V[at] = V[at] + scaled_update * (double)((const float*)(ut + UT_SLOTS))[slot];
+        }
       }
-      (void)k;
     }
   }
 }
@@ -198,7 +177,7 @@ __device__ __forceinline__ int ln_argmax(AgentD& ag, double v, const double* qs,
 }
 
 // ---- Traces::decay + Traces::update + Agent::updateQ in one sweep (see trace_pass in rlm_agent.cuh for the
-// derivation); tt = tile -> last-writer table of the from-state, bloom = features whose weight moved
+// derivation); tt = tile -> last-writer table of the from-state, ut = update table (see ln_patch_local)
 __device__ __forceinline__ void ln_tt_build(int* tt, const AgentD& ag, int lane) {
   int4* t4 = (int4*)tt;
 #pragma unroll
@@ -220,12 +199,11 @@ __device__ __forceinline__ void ln_tt_build(int* tt, const AgentD& ag, int lane)
   __syncwarp();
 }
 
-__device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, unsigned* bloom, int* tf, float* te, double* theta, int action, float rate,
-                                          double scaled_update, int lane) {
+__device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, bool track, int* tf, float* te, double* theta, int action,
+                                          float rate, double scaled_update, int lane) {
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];
-  for (int i = lane; i < BLOOM_WORDS; i += 32) bloom[i] = 0u;
-  __syncwarp();
+  // track: `ut` (cleared by the caller) takes the surviving entries
   const float tol = 0.01f;
   int w = 0;
   if (rate != 0.0f) {
@@ -254,7 +232,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, unsigned*
             __stcg(tf + pos, f);
             __stcg(te + pos, ev);
             red_add_f64(theta + f, scaled_update * (double)ev);
-            bloom_set(bloom, f);
+            if (track) ut_insert(ut, f, ev);
           }
           w += __popc(mask);
         }
@@ -282,7 +260,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, unsigned*
       __stcg(tf + pos, f);
       __stcg(te + pos, 1.0f);
       red_add_f64(theta + f, scaled_update * (double)1.0f);
-      bloom_set(bloom, f);
+      if (track) ut_insert(ut, f, 1.0f);
     }
     w = total;
   }
@@ -334,8 +312,8 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
   LPH(0);
   double* V = (double*)scr;
   int* tt = (int*)(scr + ln_v_bytes(DBL ? 1 : 0));
-  unsigned* bloom = (unsigned*)(tt + 2 * TT_SLOTS);
-  double* q_pre_a = (double*)(bloom + BLOOM_WORDS);
+  int* ut = tt + 2 * TT_SLOTS;
+  double* q_pre_a = (double*)(ut + 2 * UT_SLOTS);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   double* dec = q_pre_b + RLM_MAX_ACTIONS;
   const unsigned* rnd = rlm_rndseq_table;
@@ -357,6 +335,13 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
   const size_t pol = P.shared_policy ? 0 : (size_t)env;
   double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
   double* theta_b = DBL ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
+#ifdef RLM_TIMING  // what-if switches (results are wrong): 1 = every env gathers from ONE 512 KB table, 2 = no fence,
+  //                  4 = no re-read of updated weights before the second evaluation
+  if (D.debug_flags & 1) theta_a = ptr.theta;
+  const bool dbg_nofence = D.debug_flags & 2, dbg_nopatch = D.debug_flags & 4;
+#else
+  const bool dbg_nofence = false, dbg_nopatch = false;
+#endif
   const int kind = ag.kind;
   const int al = lane & 15;  // action of this lane in the sums (lanes 16.. = table B)
   const bool do_main = (stage != 2) && (kind == 0);
@@ -371,7 +356,13 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
     const float* vars = (is_main || stage == 2) ? ag.to_vars : ag.from_vars;
     // (kind 1: the never-populated State in a Learner's first episode, the previous episode's stale State afterwards)
     const bool null_state = is_main ? false : ((kind == 1 || stage == 1) ? ag.null_from != 0 : false);
-    h = ln_hash(rnd, vars, null_state, lane);
+    if (is_main && ag.hs_valid) {  // the tick kernel hashed the to-state (and prefetched its tiles)
+      const unsigned long long* hs = ptr.hsum + (size_t)env * 96;
+      h.s[0] = __ldcg(hs + lane); h.s[1] = __ldcg(hs + 32 + lane); h.s[2] = __ldcg(hs + 64 + lane);
+      h.null_state = false;
+    } else {
+      h = ln_hash(rnd, vars, null_state, lane);
+    }
     LPH(2);
     if (DBL || GB != 27) {
       if (is_main) ln_tt_build(tt, ag, lane);
@@ -426,13 +417,16 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
     float* te = ptr.trace_e + (size_t)env * P.trace_cap;
     double* th = table ? theta_b : theta_a;
     if (stage == 1) th = table ? ptr.dtheta + P.memory_size : ptr.dtheta;  // accumulate, apply after the all-reduce
-    const int nz = ln_trace_pass(ag, tt, bloom, tf, te, th, ag.cur_action, rate, scaled, lane);
-    if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; }
+    const bool local_patch = (stage == 0) && (ag.n_traces + 32 <= UT_MAX_ENTRIES);
+    if (local_patch) { ut_clear(ut, lane); __syncwarp(); }
+    const int nz = ln_trace_pass(ag, tt, ut, local_patch, tf, te, th, ag.cur_action, rate, scaled, lane);
+    if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; ag.hs_valid = 0; }
     sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
     __syncwarp();
     LPH(8);
-    if (stage == 0 || env < P.record_envs) __threadfence();
-    LPH(9);  // theta updates (L2 reductions) are ordered before the re-reads
+    // theta updates (L2 reductions) are ordered before re-reads: only the parity record and an overfull update table need them
+    if ((env < P.record_envs || (stage == 0 && !local_patch)) && !dbg_nofence) __threadfence();
+    LPH(9);
     if (env < P.record_envs) { if (RESIDENT) emit_record_res(ptr, hdr, env, ag, theta_a, ag.to_vars, lane); else emit_record_ool(ptr, g, env, ag, theta_a, ag.to_vars, lane); }
     if (stage == 0) {
       // the to-state becomes the from-state; Q(from, .) under the UPDATED theta (serial.cpp:55,60)
@@ -440,7 +434,12 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
       ag.from_base0[lane] = mod_m(h.s[0]);
       if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
       steps_done++;
-      ln_patch(theta_a, theta_b, bloom, h, lane, V);
+      LPH(13);
+      if (!dbg_nopatch) {
+        if (local_patch) ln_patch_local(ut, scaled, h, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
+        else ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V);  // (long trace lists: read everything again)
+      }
+      LPH(14);
       __syncwarp();
       LPH(10);
       q = ln_sums(V, DBL, lane);
@@ -463,16 +462,18 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
 }
 
 template <bool DBL>
-__global__ void __launch_bounds__(LN_WARPS * 32, 4) rlm_learn_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
+__global__ void __launch_bounds__(LN_WARPS * 32, 5) rlm_learn_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wsm = smem + (size_t)warp * ln_warp_bytes(DBL ? 1 : 0);
   const int n_ready = ptr.ready_count[tslot];
   unsigned long long steps_done = 0, sum_z = 0;
+  if (n_ready > (int)blockIdx.x) KLOG_BEGIN(1);
   // ready env k goes to warp (k / gridDim.x) of CTA (k % gridDim.x): a short list spreads over all SMs
 #pragma unroll 1
   for (int idx = warp * gridDim.x + blockIdx.x; idx < n_ready; idx += LN_WARPS * gridDim.x)
     ln_step<DBL, false, 27>(ptr, D, ptr.ready[idx], *(AgentD*)wsm, wsm + LN_AG_BYTES, nullptr, lane, stage, steps_done, sum_z, idx);
+  if (steps_done) KLOG_END(1);
   if (lane == 0 && (steps_done | sum_z)) {
     atomicAdd(&ptr.counters[1], steps_done);
     atomicAdd(&ptr.counters[2], sum_z);
@@ -486,10 +487,19 @@ cudaError_t rlm_launch_learn(const DevPtrs& ptr, const DynParams& D, int n_envs,
     cudaError_t e = is_double ? cudaFuncSetAttribute(rlm_learn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                               : cudaFuncSetAttribute(rlm_learn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (is_double) cudaFuncSetAttribute(rlm_learn_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
+    else cudaFuncSetAttribute(rlm_learn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
     attr_smem[is_double ? 1 : 0] = smem;
   }
   int grid = (n_envs + LN_WARPS - 1) / LN_WARPS;  // worst case: every env is ready
-  const int cap = n_sms * 4;                      // one resident wave; the grid-stride loop takes the rest
+  static int per_sm[2] = {0, 0};                  // resident CTAs per SM (shared memory bound)
+  if (!per_sm[is_double ? 1 : 0]) {
+    int n = 0;
+    cudaError_t e = is_double ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rlm_learn_kernel<true>, LN_WARPS * 32, smem)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rlm_learn_kernel<false>, LN_WARPS * 32, smem);
+    per_sm[is_double ? 1 : 0] = (e == cudaSuccess && n > 0) ? n : 1;
+  }
+  const int cap = n_sms * per_sm[is_double ? 1 : 0];  // one resident wave; the grid-stride loop takes the rest
   if (grid > cap) grid = cap;
   if (is_double) rlm_learn_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
   else rlm_learn_kernel<false><<<grid, LN_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
@@ -531,6 +541,12 @@ __global__ void __launch_bounds__(FU2_WARPS * 32, 2) rlm_fused2_kernel(DevPtrs p
   unsigned ticked = 0;
   unsigned long long steps_done = 0, sum_z = 0;
   unsigned long long* mt_pol = ptr.mt_pol + (size_t)env * 312;
+#ifdef RLM_TIMING  // per env: [0] cycles in ticks, [1] ticks, [2] cycles waiting for a slot, [3] cycles in learner steps, [4] steps, [5] begin_step cycles
+  long long fu_t[6] = {0, 0, 0, 0, 0, 0};
+#define FUT(i, ...) do { const long long c0_ = clock64(); __VA_ARGS__; fu_t[i] += clock64() - c0_; } while (0)
+#else
+#define FUT(i, ...) do { __VA_ARGS__; } while (0)
+#endif
   if (e.ag.need_begin) {  // (left pending by the tick-synchronous engine)
     if (lane == 0) { begin_step(e, mt_pol, D); e.ag.need_begin = 0; }
     __syncwarp();
@@ -538,34 +554,50 @@ __global__ void __launch_bounds__(FU2_WARPS * 32, 2) rlm_fused2_kernel(DevPtrs p
 #pragma unroll 1
   for (int t = 0; t < D.n_ticks; ++t) {
     if (e.phase == PH_DONE) break;
-    const int ready = envw_tick(w, ring, ptr, D, env, D.stream_off + t, lane, ticked);
+    int ready;
+    FUT(0, ready = envw_tick(w, ring, ptr, D, env, D.stream_off + t, lane, ticked));
+#ifdef RLM_TIMING
+    fu_t[1]++;
+#endif
     if (P.source == RLM_SOURCE_STREAM && D.stream_off + t >= D.stream_ticks) break;
     if (ready < 0) continue;
     // a learner step (or the end of warm-up): borrow a scratch slot of the CTA
     int slot = -1;
-    if (lane == 0) {
-      while (true) {
+    FUT(2, {
+      if (lane == 0) {
+        while (true) {
 #pragma unroll
-        for (int k = 0; k < FU2_SLOTS; ++k) {
-          const int s = (warp + k) % FU2_SLOTS;
-          if (slot < 0 && atomicCAS(&slot_busy[s], 0, 1) == 0) slot = s;
+          for (int k = 0; k < FU2_SLOTS; ++k) {
+            const int s = (warp + k) % FU2_SLOTS;
+            if (slot < 0 && atomicCAS(&slot_busy[s], 0, 1) == 0) slot = s;
+          }
+          if (slot >= 0) break;
+          __nanosleep(200);
         }
-        if (slot >= 0) break;
-        __nanosleep(200);
       }
-    }
-    slot = __shfl_sync(FULL, slot, 0);
-    ln_step<DBL, true, 9>(ptr, D, env, e.ag, slots + (size_t)slot * ln_scratch_bytes(DBL ? 1 : 0), &e, lane, 0, steps_done, sum_z, 4096);
-    __syncwarp();
-    if (lane == 0) {
-      atomicExch(&slot_busy[slot], 0);
-      begin_step(e, mt_pol, D);  // serial.cpp:55-61: the next action, DoAction, first reward term
-      e.ag.need_begin = 0;
-    }
-    __syncwarp();
+      slot = __shfl_sync(FULL, slot, 0);
+    });
+    FUT(3, {
+      ln_step<DBL, true, 9>(ptr, D, env, e.ag, slots + (size_t)slot * ln_scratch_bytes(DBL ? 1 : 0), &e, lane, 0, steps_done, sum_z, 4096);
+      __syncwarp();
+    });
+#ifdef RLM_TIMING
+    fu_t[4]++;
+#endif
+    if (lane == 0) atomicExch(&slot_busy[slot], 0);
+    FUT(5, {
+      if (lane == 0) {
+        begin_step(e, mt_pol, D);  // serial.cpp:55-61: the next action, DoAction, first reward term
+        e.ag.need_begin = 0;
+      }
+      __syncwarp();
+    });
   }
   __syncwarp();
   envw_stage_out(g, &e, lane);
+#ifdef RLM_TIMING
+  if (lane == 0 && env < 4096) for (int i = 0; i < 6; ++i) g_phase_clk[env * 16 + i] = fu_t[i];
+#endif
   if (lane == 0) {
     if (ticked) atomicAdd(&ptr.counters[0], (unsigned long long)ticked);
     if (steps_done | sum_z) { atomicAdd(&ptr.counters[1], steps_done); atomicAdd(&ptr.counters[2], sum_z); }

@@ -69,7 +69,8 @@ struct alignas(16) AgentD {
   // next episode's first action is chosen from -- and its first transition starts at -- this state (serial.cpp:24-25,55,60)
   float prev_vars[RLM_N_STATE_MAX + 3];
   int prev_null;
-  int pad[3];
+  int hs_valid;  // the tick kernel has stored the to-state's tile-hash sums in DevPtrs::hsum (and prefetched the tiles into L2)
+  int pad[2];
 };
 
 struct EnvHdr {
@@ -131,8 +132,12 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int n_ticks;
   int stream_ticks;   // ticks in the resident stream chunk
   int stream_off;     // first tick of the chunk this launch consumes
-  int reserved0;      // (was a per-tick CTA barrier switch of the persistent engine; unused)
+  int env0;           // tick-synchronous engine: first env of the sub-batch this launch covers
   int backtest;       // 1: Backtester::_step (serial.cpp:121-137): act on the current state, never learn
+  int n_sub;          // ... and its size (0 = the whole batch).  Sub-batches run on their own streams (rlm_api.cu)
+  int sub_idx;        // index of the sub-batch (timeline probe of the RLM_TIMING build)
+  int debug_flags;    // RLM_TIMING build only (RLM_DEBUG_FLAGS): what-if switches of tools/timeline_probe.py; results are wrong with any set
+  int pad;
 };
 
 struct DevPtrs {
@@ -149,6 +154,7 @@ struct DevPtrs {
   int* record_count;           // [record_envs]
   unsigned long long* counters;  // [8]: ticks, steps, sum_traces, terminal, err
   unsigned* occ;                 // [n_policies][occ_words] occupancy bitmap: bit f set <=> theta[f] was ever updated
+  unsigned long long* hsum;      // [n_envs][3][32] partial tile-hash sums of the to-state (lane j = tiling j), written by the tick kernel
   int* ready;                    // [n_envs] env indices that need the agent kernel this tick
   int* ready_count;              // [ticks of the current run call]
   // persistent engine

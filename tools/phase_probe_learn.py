@@ -35,4 +35,5 @@ for rep in range(3):
         np.percentile(a[:, 0] - a[:, 0].min(), 50), np.percentile(a[:, 0] - a[:, 0].min(), 99)))
     for i, n in enumerate(names):
         print("  %-32s mean %8.0f  p50 %8.0f  p90 %8.0f  max %8.0f" % (n, d[:, i].mean(), np.percentile(d[:, i], 50), np.percentile(d[:, i], 90), d[:, i].max()))
+    print('  patch split: advance state %.0f | local patch %.0f | syncwarp %.0f' % ((a[:, 13] - a[:, 9]).mean(), (a[:, 14] - a[:, 13]).mean(), (a[:, 10] - a[:, 14]).mean()))
 m.close()
