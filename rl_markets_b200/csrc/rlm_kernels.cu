@@ -310,6 +310,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams D, int tslot, int only_begin) {
   const int b = D.env0 + blockIdx.x * THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (!only_begin) KLOG_BEGIN(0);
   int ready = -1;
   unsigned ticked = 0, errs = 0;
   if (b < (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) {
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
     base = __shfl_sync(FULL, base, leader);
     if (ready >= 0) ptr.ready[base + __popc(m & ((1u << lane) - 1u))] = b;
   }
+  if (!only_begin) KLOG_END(0);
   const unsigned tm = __ballot_sync(FULL, ticked != 0);
   unsigned em = errs;
   for (int o = 16; o > 0; o >>= 1) em |= __shfl_xor_sync(FULL, em, o);

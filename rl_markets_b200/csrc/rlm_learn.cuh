@@ -93,26 +93,27 @@ __device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every 
   while (atomicCAS(&ut[slot], HS_EMPTY, f) != HS_EMPTY) slot = (slot + 1) & (UT_SLOTS - 1);
   ((float*)(ut + UT_SLOTS))[slot] = ev;
 }
-__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
+template <bool POW2>
+__device__ __forceinline__ void ln_patch_local_t(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
   const int A = P.n_actions;
-  const bool pow2 = P.m_pow2 != 0;
-#pragma unroll 1
-  for (int g = 0; g < 3; ++g) {
+  const float* uv = (const float*)(ut + UT_SLOTS);
 #pragma unroll
-    for (int a = 0; a < RLM_MAX_ACTIONS; ++a) {
-      const unsigned long long sum = h.s[g] + P.rg[g][a];
-      const int f = h.null_state ? 0 : (pow2 ? (int)((unsigned)sum & (unsigned)(P.memory_size - 1)) : mod_m(sum));
-      if (a < A) {
-        unsigned slot = ut_hash(f);
-        int k = ut[slot];
-        while (k != HS_EMPTY && k != f) { slot = (slot + 1) & (UT_SLOTS - 1); k = ut[slot]; }
-        if (k == f) {
-          const int at = a * LN_VROW + g * 32 + lane;
-          V[at] = V[at] + scaled_update * (double)((const float*)(ut + UT_SLOTS))[slot];
-        }
+  for (int k = 0; k < 3 * RLM_MAX_ACTIONS; ++k) {  // (unrolled: the sums stay in registers)
+    if ((k % RLM_MAX_ACTIONS) < A) {
+      const int f = ln_tile<POW2>(h, k);
+      unsigned slot = ut_hash(f);
+      int key = ut[slot];
+      while (key != HS_EMPTY && key != f) { slot = (slot + 1) & (UT_SLOTS - 1); key = ut[slot]; }
+      if (key == f) {
+        const int at = (k % RLM_MAX_ACTIONS) * LN_VROW + (k / RLM_MAX_ACTIONS) * 32 + lane;
+        V[at] = V[at] + scaled_update * (double)uv[slot];
       }
     }
   }
+}
+__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
+  if (P.m_pow2) ln_patch_local_t<true>(ut, scaled_update, h, lane, V);
+  else ln_patch_local_t<false>(ut, scaled_update, h, lane, V);
 }
 
 // ---- exact-order sum of agent.cpp:117-135 over one action row of raw weights: 16 blocks of 8; block b+1 is loaded

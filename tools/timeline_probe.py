@@ -1,14 +1,15 @@
 #!/usr/bin/env python3
 """Launch timeline of the tick-synchronous engine with sub-batch streams (RLM_TIMING build): when did each env tick
 kernel and learner kernel of each sub-batch start and end (globaltimer, ns)?
-    RLM_SUBBATCHES=2 RLM_LIB_PATH=rl_markets_b200/librlm_timing.so python tools/timeline_probe.py [pretrain] [envs] [M]"""
+    RLM_SUBBATCHES=2 RLM_LIB_PATH=rl_markets_b200/librlm_timing.so python tools/timeline_probe.py [pretrain] [envs] [M] [algo]"""
 import ctypes as C, sys, os, numpy as np
 sys.path.insert(0, '.')
 from rl_markets_b200 import config, lib
 pre = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
-y = config.example_dict(**{"learning.memory_size": M, "learning.algorithm": "q_learn"})
+algo = sys.argv[4] if len(sys.argv) > 4 else "q_learn"
+y = config.example_dict(**{"learning.memory_size": M, "learning.algorithm": algo})
 cfg = config.from_dict(y, n_envs=B, flow_seed=1, dt_ms=1)
 m = lib.BatchedMarket(cfg)
 left = pre
@@ -25,7 +26,7 @@ a = np.frombuffer(buf, dtype=np.uint64).reshape(256, 8, 2, 2).astype(np.int64)
 S = int(os.environ.get("RLM_SUBBATCHES", "4"))
 t0 = min(a[t, s, 0, 0] for t in range(64) for s in range(S) if a[t, s, 0, 1] > 0)
 print("sub-batches %d; times in us since the first env kernel of the call" % S)
-for t in list(range(20, 28)):
+for t in list(range(20, 24)):
     row = []
     for s in range(S):
         e0, e1, l0, l1 = a[t, s, 0, 0], a[t, s, 0, 1], a[t, s, 1, 0], a[t, s, 1, 1]
