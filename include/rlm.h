@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RLM_ABI_VERSION 2
+#define RLM_ABI_VERSION 3
 
 typedef enum rlm_status {
   RLM_OK = 0,
@@ -195,8 +195,8 @@ int rlm_get_rho(rlm_handle h, double* out /* [n_envs] */);
    handles must agree in device, n_envs / shared_policy, memory_size and algorithm family; traces and env state of `dst`
    are untouched. */
 int rlm_copy_theta(rlm_handle dst, rlm_handle src);
-/* Diagnostic (no reference counterpart): number of weights of env b's table A that have ever been written, i.e. the
-   population of the occupancy bitmap the learner kernel uses to skip gathers of exact zeros (independent policies). */
+/* Diagnostic (no reference counterpart): number of weights of env b's table A that are not +0.0, i.e. how far the
+   table has filled up (independent policies). */
 int rlm_get_occupancy(rlm_handle h, int32_t* out /* [n_envs] */);
 
 int rlm_handle_terminal(rlm_handle h, int32_t episode);
@@ -219,6 +219,27 @@ int rlm_device_ptrs(rlm_handle h, void** theta, void** dtheta, int64_t* n_double
  * On one GPU rlm_run_ticks does the same without the collective. */
 int rlm_shared_tick_accumulate(rlm_handle h);
 int rlm_apply_dtheta(rlm_handle h);
+/* ---- split surface: the reference's Environment::step / Agent::update seam, batched ------------------------------
+ * rlm_run_ticks fuses the whole of experiment::serial::Learner::_step (src/experiment/serial.cpp:53-70).  These three
+ * calls expose its parts, so that an external policy can supply the actions and an external consumer can read every
+ * transition; driven in the order below they reproduce rlm_run_ticks bit for bit (tests/test_gpu_split.py):
+ *
+ *   rlm_env_step(h, NULL, ..)        Runner::RunEpisode: environment.Initialise()              serial.cpp:18-25
+ *   rlm_agent_update(h, NULL)        ... Q(first from-state, .) for the first action
+ *   repeat:
+ *     rlm_act(h, actions)            int action = m->action(*last_state)                       serial.cpp:60,  include/rl/agent.h:60
+ *     rlm_env_step(h, actions, r, t) environment.performAction(action) + getReward()           serial.cpp:61,66, include/environment/base.h:132
+ *     rlm_agent_update(h, delta)     state->newState(env); m->HandleTransition(...)            serial.cpp:64-67, include/rl/agent.h:62-67
+ *
+ * Every env advances by ONE learner step per rlm_env_step (its own K >= 1 market ticks, base.cpp:285-305); envs are
+ * therefore not tick-aligned afterwards, which is why this surface needs source = generator.  actions_out[b] / the
+ * action applied is -1 for an env whose episode is over.  rlm_env_step(h, actions != NULL) without a preceding rlm_act
+ * is the "external policy" form: no generator draw is consumed.  Independent policies only. */
+int rlm_act(rlm_handle h, int32_t* actions_out /* [n_envs] */);
+int rlm_env_step(rlm_handle h, const int32_t* actions /* [n_envs] or NULL = the agent's own */, double* reward_out /* [n_envs] or NULL */,
+                 uint8_t* terminal_out /* [n_envs] or NULL */);
+int rlm_agent_update(rlm_handle h, double* delta_out /* [n_envs] TD error of each env's last transition, or NULL */);
+
 /* measurement hooks (bench.py): CUDA-event durations of the env-tick and agent kernels, summed over launches */
 int rlm_set_profiling(rlm_handle h, int32_t on);
 int rlm_get_kernel_times(rlm_handle h, double* env_ms, double* agent_ms, int64_t* env_launches, int64_t* agent_launches);

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -72,7 +73,26 @@ struct rlm_handle_s {
   cudaEvent_t ev_fork = nullptr, ev_join[RLM_MAX_SUB] = {};
 };
 
+// The kernels read their per-handle constants from ONE __constant__ block (rlm_env.cuh: P).  g_params_owner says whose
+// they are; another handle takes the block over only after everything launched so far has finished (device-wide
+// synchronisation), and every entry point that launches kernels holds g_api_mu while it does so -- so two handles on
+// one GPU, from one or several host threads, are safe; alternating between them costs a device synchronisation per switch.
 static const rlm_handle_s* g_params_owner = nullptr;
+static std::recursive_mutex g_api_mu;
+#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock_(g_api_mu)
+
+// pinned + device staging area for per-env columns (grown on demand)
+static int split_scratch(rlm_handle_s* h, size_t bytes) {
+  if (bytes > h->gather_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_gather); if (h->h_gather) cudaFreeHost(h->h_gather);
+    h->d_gather = nullptr; h->h_gather = nullptr; h->gather_cap = 0;
+    CK(cudaMalloc(&h->d_gather, bytes));
+    CK(cudaMallocHost(&h->h_gather, bytes));
+    h->gather_cap = bytes;
+  }
+  return RLM_OK;
+}
 
 extern "C" {
 
@@ -241,13 +261,17 @@ static cudaError_t launch_agent_any(rlm_handle_s* h, const DynParams& d, int tsl
 
 static int upload_params(rlm_handle_s* h) {
   if (g_params_owner != h) {
+    CK(cudaDeviceSynchronize());  // kernels of the previous owner still read its constants
     CK(rlm_upload_params(&h->hp));
     g_params_owner = h;
   }
   return RLM_OK;
 }
 
+static int create_impl(const rlm_config* cfg, rlm_handle_s* h);
+
 int rlm_create(const rlm_config* cfg, rlm_handle* out) {
+  API_LOCK;
   if (!cfg || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
   int ndev = 0;
@@ -258,14 +282,36 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   if (cfg->device < 0 || cfg->device >= ndev) return fail(RLM_ERR_INVALID_ARGUMENT, "bad device ordinal");
   rlm_handle_s* h = new rlm_handle_s();
   h->cfg = *cfg;
+  memset(&h->ptr, 0, sizeof(h->ptr));
   int rc = derive(h);
   if (rc != RLM_OK) { delete h; return rc; }
+  rc = create_impl(cfg, h);
+  if (rc != RLM_OK) {  // every stream, event and device buffer made so far goes back
+    const std::string keep = g_err;
+    rlm_destroy(h);
+    g_err = keep;
+    return rc;
+  }
+  *out = h;
+  return RLM_OK;
+}
+
+static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
   CK(cudaSetDevice(cfg->device));
+  {
+    // theta dominates: fail with a readable message instead of an out-of-memory half way through the allocations
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const double need = (double)(cfg->shared_policy ? 1 : cfg->n_envs) * (double)h->hp.memory_size * 8.0 * (h->hp.is_double ? 2 : 1) +
+                        (double)cfg->n_envs * ((double)h->hp.env_stride + 8.0 * h->hp.trace_cap + 2.0 * 312 * 8 + 768);
+    if (need > (double)free_b)
+      return fail(RLM_ERR_INVALID_ARGUMENT, "n_envs x memory_size needs " + std::to_string((long long)(need / 1e6)) + " MB of device memory, " +
+                                                std::to_string((long long)(free_b / 1e6)) + " MB are free");
+  }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const DevParams& p = h->hp;
   h->n_policies = cfg->shared_policy ? 1 : cfg->n_envs;
   h->env_bytes = (size_t)p.env_stride * cfg->n_envs;
-  memset(&h->ptr, 0, sizeof(h->ptr));
   CK(cudaMalloc(&h->ptr.env, h->env_bytes));
   size_t th_bytes = (size_t)h->n_policies * (size_t)p.memory_size * 8;
   CK(cudaMalloc(&h->ptr.theta, th_bytes));
@@ -299,7 +345,7 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
   CK(cudaMalloc(&h->ptr.counters, 8 * 8));
   CK(cudaMemsetAsync(h->ptr.counters, 0, 8 * 8, h->stream));
   g_params_owner = nullptr;
-  rc = upload_params(h);
+  int rc = upload_params(h);
   if (rc != RLM_OK) return rc;
   CK(rlm_launch_init(h->ptr, cfg->n_envs, 0, h->stream));
   CK(rlm_launch_seed(h->ptr, cfg->n_envs, cfg->random_seed, h->stream));
@@ -360,13 +406,14 @@ int rlm_create(const rlm_config* cfg, rlm_handle* out) {
     if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
+  // (device-wide, and it stays for the lifetime of the hosting process)
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   CK(cudaStreamSynchronize(h->stream));
-  *out = h;
   return RLM_OK;
 }
 
 int rlm_destroy(rlm_handle h) {
+  API_LOCK;
   if (!h) return RLM_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
@@ -395,6 +442,7 @@ int rlm_destroy(rlm_handle h) {
 }
 
 int rlm_set_stream(rlm_handle h, void* cuda_stream) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
@@ -405,6 +453,7 @@ int rlm_set_stream(rlm_handle h, void* cuda_stream) {
 }
 
 int rlm_reset(rlm_handle h) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   int rc = upload_params(h);
@@ -424,13 +473,14 @@ int rlm_set_mode(rlm_handle h, int32_t mode) {
 }
 
 int rlm_new_env(rlm_handle h, const rlm_flow_params* flow) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   if (flow) {
     CK(cudaStreamSynchronize(h->stream));  // running kernels read the old parameters from constant memory
     h->cfg.flow = *flow;
     h->hp.flow = *flow;
-    if (g_params_owner == h) g_params_owner = nullptr;  // force the re-upload
+    if (g_params_owner == h) g_params_owner = nullptr;  // force the re-upload (after a device-wide synchronisation)
   }
   int rc = upload_params(h);
   if (rc) return rc;
@@ -441,6 +491,7 @@ int rlm_new_env(rlm_handle h, const rlm_flow_params* flow) {
 }
 
 int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks) {
+  API_LOCK;
   if (!h || !msgs || n_ticks <= 0) return fail(RLM_ERR_INVALID_ARGUMENT, "bad arguments");
   if (h->cfg.source != RLM_SOURCE_STREAM) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was created with source = generator");
   CK(cudaSetDevice(h->cfg.device));
@@ -477,6 +528,7 @@ int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks) {
 static int run_ticks_impl(rlm_handle h, int32_t n_ticks);
 
 int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
+  API_LOCK;
   if (!h || n_ticks < 0) return fail(RLM_ERR_INVALID_ARGUMENT, "bad arguments");
   if (n_ticks == 0) return RLM_OK;
   CK(cudaSetDevice(h->cfg.device));
@@ -605,6 +657,7 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
 }
 
 int rlm_sync(rlm_handle h) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
@@ -625,6 +678,7 @@ int rlm_sync(rlm_handle h) {
 }
 
 int rlm_get_counters(rlm_handle h, rlm_counters* out) {
+  API_LOCK;
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
@@ -646,6 +700,7 @@ static int fetch_hdrs(rlm_handle h, int env0, int n, std::vector<EnvHdr>& out) {
 }
 
 int rlm_get_stats(rlm_handle h, int32_t env0, int32_t n, rlm_env_stats* out) {
+  API_LOCK;
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   std::vector<EnvHdr> v;
   int rc = fetch_hdrs(h, env0, n, v);
@@ -665,6 +720,7 @@ int rlm_get_stats(rlm_handle h, int32_t env0, int32_t n, rlm_env_stats* out) {
 
 // packed column read-back: gather kernel -> pinned staging -> caller's buffer (B values over PCIe, not B headers)
 static int fetch_column(rlm_handle h, int what, void* out, size_t bytes) {
+  API_LOCK;
   CK(cudaSetDevice(h->cfg.device));
   int rc = upload_params(h);
   if (rc) return rc;
@@ -692,8 +748,18 @@ int rlm_get_reward(rlm_handle h, double* out) {
   return fetch_column(h, 0, out, (size_t)h->cfg.n_envs * sizeof(double));
 }
 int rlm_get_occupancy(rlm_handle h, int32_t* out) {
+  API_LOCK;
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
-  return fetch_column(h, 4, out, (size_t)h->cfg.n_envs * sizeof(int32_t));
+  if (h->cfg.shared_policy) return fail(RLM_ERR_UNSUPPORTED, "rlm_get_occupancy is per env (independent policies)");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t bytes = (size_t)h->cfg.n_envs * sizeof(int32_t);
+  int rc = split_scratch(h, bytes);
+  if (rc) return rc;
+  CK(rlm_launch_count_nonzero(h->ptr.theta, h->cfg.memory_size, h->cfg.n_envs, (int*)h->d_gather, h->stream));
+  CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_gather, bytes);
+  return RLM_OK;
 }
 int rlm_get_rho(rlm_handle h, double* out) {
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
@@ -705,6 +771,7 @@ int rlm_get_actions(rlm_handle h, int32_t* out) {
 }
 
 int rlm_handle_terminal(rlm_handle h, int32_t episode) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   int rc = upload_params(h);
@@ -730,6 +797,7 @@ int rlm_go_greedy(rlm_handle h) {
 }
 
 int rlm_read_theta(rlm_handle h, int32_t policy, int32_t table, double* out, int64_t n) {
+  API_LOCK;
   if (!h || !out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   if (policy < 0 || policy >= h->n_policies || n < 0 || n > h->cfg.memory_size) return fail(RLM_ERR_INVALID_ARGUMENT, "bad policy index / length");
   double* src = table == 0 ? h->ptr.theta : h->ptr.theta_b;
@@ -740,6 +808,7 @@ int rlm_read_theta(rlm_handle h, int32_t policy, int32_t table, double* out, int
   return RLM_OK;
 }
 int rlm_write_theta(rlm_handle h, int32_t policy, int32_t table, const double* in, int64_t n) {
+  API_LOCK;
   if (!h || !in) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   if (policy < 0 || policy >= h->n_policies || n < 0 || n > h->cfg.memory_size) return fail(RLM_ERR_INVALID_ARGUMENT, "bad policy index / length");
   double* dst = table == 0 ? h->ptr.theta : h->ptr.theta_b;
@@ -752,10 +821,12 @@ int rlm_write_theta(rlm_handle h, int32_t policy, int32_t table, const double* i
     const int dense = (int)h->cfg.memory_size;
     CK(cudaMemcpy(h->ptr.env + (size_t)policy * h->hp.env_stride + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), &dense, 4, cudaMemcpyHostToDevice));
   }
+  CK(cudaDeviceSynchronize());
   return RLM_OK;
 }
 
 int rlm_copy_theta(rlm_handle dst, rlm_handle src) {
+  API_LOCK;
   if (!dst || !src) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   if (dst->cfg.device != src->cfg.device || dst->n_policies != src->n_policies || dst->cfg.memory_size != src->cfg.memory_size ||
       dst->hp.is_double != src->hp.is_double || dst->cfg.shared_policy != src->cfg.shared_policy)
@@ -771,10 +842,12 @@ int rlm_copy_theta(rlm_handle dst, rlm_handle src) {
     CK(cudaMemcpy2D(dst->ptr.env + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), dst->hp.env_stride,
                     src->ptr.env + offsetof(EnvHdr, ag) + offsetof(AgentD, n_occ), src->hp.env_stride, 4, src->cfg.n_envs,
                     cudaMemcpyDeviceToDevice));
+  CK(cudaDeviceSynchronize());  // device-to-device copies do not block the host: dst may be run right away
   return RLM_OK;
 }
 
 int rlm_read_records(rlm_handle h, int32_t env, rlm_step_record* out, int32_t cap, int32_t* n_out) {
+  API_LOCK;
   if (!h || !out || !n_out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
   if (env < 0 || env >= h->hp.record_envs) return fail(RLM_ERR_INVALID_ARGUMENT, "env is not recorded (cfg.record_envs)");
   CK(cudaSetDevice(h->cfg.device));
@@ -799,6 +872,7 @@ int rlm_device_ptrs(rlm_handle h, void** theta, void** dtheta, int64_t* n_double
 // accumulated into dtheta.  The caller all-reduces dtheta (rlm_device_ptrs) across ranks when the policy
 // spans GPUs, then calls rlm_apply_dtheta.
 int rlm_shared_tick_accumulate(rlm_handle h) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->cfg.shared_policy) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was not created with shared_policy");
   CK(cudaSetDevice(h->cfg.device));
@@ -822,6 +896,7 @@ int rlm_shared_tick_accumulate(rlm_handle h) {
 // Shared policy, phase B: theta += dtheta; dtheta = 0; Q(from, .) under the new theta for the envs that
 // stepped; then their action selection (the trailing env pass).
 int rlm_apply_dtheta(rlm_handle h) {
+  API_LOCK;
   if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->cfg.shared_policy) return fail(RLM_ERR_INVALID_ARGUMENT, "handle was not created with shared_policy");
   CK(cudaSetDevice(h->cfg.device));
@@ -834,6 +909,107 @@ int rlm_apply_dtheta(rlm_handle h) {
   CK(launch_agent_any(h, h->shared_dyn, 0, 2));
   CK(rlm_launch_env(h->ptr, h->shared_dyn, h->cfg.n_envs, 0, 1, h->env_variant, h->stream));
   h->launches += 3;
+  return RLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split surface: the reference's Environment::step / Agent::update seam, batched.
+static int split_check(rlm_handle h) {
+  if (!h) return fail(RLM_ERR_INVALID_ARGUMENT, "null handle");
+  if (h->cfg.shared_policy) return fail(RLM_ERR_UNSUPPORTED, "the split surface drives independent policies (shared policy: rlm_shared_tick_accumulate / rlm_apply_dtheta)");
+  if (h->cfg.source != RLM_SOURCE_GENERATOR) return fail(RLM_ERR_UNSUPPORTED, "the split surface needs source = generator: envs consume different numbers of ticks per step");
+  if (h->dyn.backtest) return fail(RLM_ERR_UNSUPPORTED, "the split surface runs Learner::_step (train mode)");
+  return RLM_OK;
+}
+static DynParams split_dyn(rlm_handle h) {
+  DynParams d = h->dyn;
+  d.alpha = h->alpha; d.eps = h->eps; d.tau = h->tau; d.n_ticks = 1;
+  d.hold = 1;
+  return d;
+}
+
+int rlm_act(rlm_handle h, int32_t* actions_out) {
+  API_LOCK;
+  int rc = split_check(h);
+  if (rc) return rc;
+  if (!actions_out) return fail(RLM_ERR_INVALID_ARGUMENT, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = upload_params(h);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->cfg.n_envs * 4;
+  rc = split_scratch(h, bytes);
+  if (rc) return rc;
+  CK(rlm_launch_act(h->ptr, split_dyn(h), h->cfg.n_envs, (int*)h->d_gather, h->stream));
+  CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(actions_out, h->h_gather, bytes);
+  h->launches += 1;
+  return RLM_OK;
+}
+
+int rlm_env_step(rlm_handle h, const int32_t* actions, double* reward_out, uint8_t* terminal_out) {
+  API_LOCK;
+  int rc = split_check(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->cfg.device));
+  rc = upload_params(h);
+  if (rc) return rc;
+  const int B = h->cfg.n_envs;
+  rc = split_scratch(h, (size_t)B * 16);
+  if (rc) return rc;
+  const DynParams d = split_dyn(h);
+  int* d_actions = nullptr;
+  if (actions) {
+    d_actions = (int*)h->d_gather;
+    memcpy(h->h_gather, actions, (size_t)B * 4);
+    CK(cudaMemcpyAsync(d_actions, h->h_gather, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(rlm_launch_apply(h->ptr, d, B, d_actions, h->stream));
+  h->launches += 1;
+  // performAction's do-while for every env that is inside a step (or Initialise for envs that are warming up): tick
+  // until each one has reached its step end.  Envs on hold do not tick; all step ends of this call share ONE ready list.
+  CK(cudaMemsetAsync(h->ptr.ready_count, 0, 4, h->stream));
+  for (int guard = 0; guard < (1 << 22); ++guard) {
+    CK(cudaMemsetAsync(h->ptr.counters + 5, 0, 8, h->stream));
+    CK(rlm_launch_env(h->ptr, d, B, 0, 0, h->env_variant, h->stream));
+    h->launches += 1;
+    unsigned long long running = 0;
+    CK(cudaMemcpyAsync(&running, h->ptr.counters + 5, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (running == 0) break;
+  }
+  if (reward_out || terminal_out) {
+    double* d_rew = (double*)h->d_gather;
+    unsigned char* d_term = (unsigned char*)h->d_gather + (size_t)B * 8;
+    CK(rlm_launch_step_out(h->ptr, B, d_rew, d_term, nullptr, h->stream));
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)B * 9, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (reward_out) memcpy(reward_out, h->h_gather, (size_t)B * 8);
+    if (terminal_out) memcpy(terminal_out, (unsigned char*)h->h_gather + (size_t)B * 8, (size_t)B);
+  }
+  return RLM_OK;
+}
+
+int rlm_agent_update(rlm_handle h, double* delta_out) {
+  API_LOCK;
+  int rc = split_check(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->cfg.device));
+  rc = upload_params(h);
+  if (rc) return rc;
+  const int B = h->cfg.n_envs;
+  // State::newState + Agent::HandleTransition for the envs on the ready list of the last rlm_env_step
+  CK(launch_agent_any(h, split_dyn(h), 0, 0));
+  CK(cudaMemsetAsync(h->ptr.ready_count, 0, 4, h->stream));
+  h->launches += 1;
+  if (delta_out) {
+    rc = split_scratch(h, (size_t)B * 8);
+    if (rc) return rc;
+    CK(rlm_launch_step_out(h->ptr, B, nullptr, nullptr, (double*)h->d_gather, h->stream));
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(delta_out, h->h_gather, (size_t)B * 8);
+  }
   return RLM_OK;
 }
 
@@ -873,12 +1049,14 @@ static int test_setup(const rlm_config* cfg, rlm_handle_s& tmp) {
   int rc = derive(&tmp);
   if (rc) return rc;
   CK(cudaSetDevice(cfg->device));
+  CK(cudaDeviceSynchronize());
   g_params_owner = nullptr;
   CK(rlm_upload_params(&tmp.hp));
   return RLM_OK;
 }
 
 int rlm_test_to_ticks(const rlm_config* cfg, const double* px, int32_t n, int32_t* out) {
+  API_LOCK;
   rlm_handle_s tmp;
   int rc = test_setup(cfg, tmp);
   if (rc) return rc;
@@ -891,6 +1069,7 @@ int rlm_test_to_ticks(const rlm_config* cfg, const double* px, int32_t n, int32_
   return RLM_OK;
 }
 int rlm_test_to_price(const rlm_config* cfg, const int32_t* ticks, int32_t n, double* out) {
+  API_LOCK;
   rlm_handle_s tmp;
   int rc = test_setup(cfg, tmp);
   if (rc) return rc;
@@ -903,6 +1082,7 @@ int rlm_test_to_price(const rlm_config* cfg, const int32_t* ticks, int32_t n, do
   return RLM_OK;
 }
 int rlm_test_tiles(const rlm_config* cfg, const float* vars, int32_t n, int32_t* out) {
+  API_LOCK;
   rlm_handle_s tmp;
   int rc = test_setup(cfg, tmp);
   if (rc) return rc;
@@ -916,6 +1096,7 @@ int rlm_test_tiles(const rlm_config* cfg, const float* vars, int32_t n, int32_t*
   return RLM_OK;
 }
 int rlm_test_order(int64_t size, int64_t q_head, const rlm_order_op* ops, int32_t n_ops, rlm_order_state* out) {
+  API_LOCK;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RLM_ERR_NO_DEVICE, "no CUDA device (no CPU fallback)");
   if (size <= 0) return fail(RLM_ERR_RUNTIME, "Order size must be non-zero and positive.");  // order.cpp:24-25
@@ -932,6 +1113,7 @@ int rlm_test_order(int64_t size, int64_t q_head, const rlm_order_op* ops, int32_
   return RLM_OK;
 }
 int rlm_test_rolling_mean(int32_t window, const double* vals, int32_t n, double* out) {
+  API_LOCK;
   rlm_config cfg;
   rlm_config_default(&cfg);
   cfg.memory_size = 1024; cfg.algorithm = RLM_ALGO_Q_LEARN;

@@ -188,6 +188,22 @@ __global__ void rlm_gather_kernel(DevPtrs ptr, int what, void* out) {
     for (int k = 0; k < P.n_state_vars; ++k) ((float*)out)[(size_t)b * P.n_state_vars + k] = e->ag.from_vars[k];
 }
 
+// rlm_get_occupancy: weights of table A that are not (bitwise) +0.0, one CTA per policy
+__global__ void rlm_count_nonzero_kernel(const double* theta, long long M, int* out) {
+  const double* th = theta + (size_t)blockIdx.x * (size_t)M;
+  int n = 0;
+  for (long long i = threadIdx.x; i < M; i += blockDim.x) n += (__double_as_longlong(__ldcs(th + i)) != 0ll) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
+  __shared__ int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w]; out[blockIdx.x] = t; }
+}
+cudaError_t rlm_launch_count_nonzero(const double* theta, long long M, int n_policies, int* out, cudaStream_t st) {
+  rlm_count_nonzero_kernel<<<n_policies, 256, 0, st>>>(theta, M, out);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // parity record (include/rlm_record.h); lane 0 fills everything but the trace hash
 // `vars`: the state written to the record (to-state of a learner step; decision state of a backtest step)
@@ -216,15 +232,19 @@ __device__ __noinline__ void fill_record(rlm_step_record* r, const EnvHdr& e, co
   r->trace_hash = thash;
 }
 
-// Learner::_step up to the first NextState of performAction (serial.cpp:55-61, base.cpp:254-284).
-// Needs ag.q_from / qb_from.  Returns false when the episode is over.
-__device__ __noinline__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, const DynParams& D) {
+// Learner::_step up to the first NextState of performAction (serial.cpp:55-61, base.cpp:254-284), in its two halves:
+//   begin_select  Agent::action(*last_state) -- or the end of the episode (isTerminal, ClearInventory serial.cpp:31)
+//   begin_apply   Base::performAction(action) up to its do-while (DoAction, CheckOrders, UpdateStats, first reward term)
+// Needs ag.q_from / qb_from.  begin_select returns the action, or -1 when the episode is over.
+__device__ __noinline__ int begin_select(EnvHdr& e, unsigned long long* mt_pol, const DynParams& D) {
   if (is_terminal(e)) {
     clear_inventory(e);  // Runner::RunEpisode, serial.cpp:31
     e.phase = PH_DONE;
-    return false;
+    return -1;
   }
-  int a = policy_action(e.ag, e.ag.q_from, e.ag.qb_from, mt_pol, D);
+  return policy_action(e.ag, e.ag.q_from, e.ag.qb_from, mt_pol, D);
+}
+__device__ __noinline__ void begin_apply(EnvHdr& e, int a) {
   e.ag.cur_action = a;
   e.last_action = a;
   e.lo_vol_step = 0;
@@ -236,7 +256,80 @@ __device__ __noinline__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, c
   e.agg_r = get_reward(e);
   e.agg_pnl = e.pnl_step;
   e.agg_mpm = 0.0;
+  e.ag.kind = 3;  // inside performAction's loop (0 / 1 = the step / the warm-up has ended and waits for the learner)
+}
+__device__ __forceinline__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol, const DynParams& D) {
+  if (e.ag.kind == 4) { begin_apply(e, e.ag.cur_action); return true; }  // (rlm_act already drew the action)
+  const int a = begin_select(e, mt_pol, D);
+  if (a < 0) return false;
+  begin_apply(e, a);
   return true;
+}
+// split surface: is this env waiting for rlm_agent_update (its step or its warm-up has ended) or for rlm_env_step to
+// apply an action?  Such envs do not tick under DynParams::hold.
+__device__ __forceinline__ bool env_on_hold(const EnvHdr& e) {
+  return e.phase == PH_RUN && (e.ag.need_begin || e.ag.kind == 0 || e.ag.kind == 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split surface (include/rlm.h: rlm_act / rlm_env_step / rlm_agent_update), one thread per env, straight on the
+// record in HBM (this is the interoperability path, not the training loop).
+// rlm_act: Agent::action for every env at a decision point; actions[b] = -1 elsewhere (and at the end of an episode).
+__global__ void rlm_act_kernel(DevPtrs ptr, DynParams D, int* actions) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.n_envs) return;
+  EnvHdr& e = *(EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
+  int a = -1;
+  if (e.phase == PH_RUN && e.ag.need_begin) {
+    if (e.ag.kind == 4) a = e.ag.cur_action;  // already selected, not applied yet
+    else {
+      a = begin_select(e, ptr.mt_pol + (size_t)b * 312, D);
+      if (a >= 0) { e.ag.cur_action = a; e.ag.kind = 4; }
+      else e.ag.need_begin = 0;
+    }
+  }
+  actions[b] = a;
+}
+// first half of rlm_env_step: Base::performAction(actions[b]) up to its do-while for every env at a decision point.
+// actions == nullptr: the agent's own choice (rlm_act semantics, selected here if rlm_act was not called).
+__global__ void rlm_apply_kernel(DevPtrs ptr, DynParams D, const int* actions) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.n_envs) return;
+  EnvHdr& e = *(EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
+  if (e.phase != PH_RUN || !e.ag.need_begin) return;
+  int a;
+  if (e.ag.kind == 4) a = actions ? actions[b] : e.ag.cur_action;
+  else if (actions) {  // external policy: Learner::_step without Agent::action (no generator draw)
+    if (is_terminal(e)) { clear_inventory(e); e.phase = PH_DONE; e.ag.need_begin = 0; return; }
+    a = actions[b];
+  } else {
+    a = begin_select(e, ptr.mt_pol + (size_t)b * 312, D);
+    if (a < 0) { e.ag.need_begin = 0; return; }
+  }
+  if (a < 0 || a >= P.n_actions) { e.err |= ERR_BAD_PRICE; a = 0; }
+  begin_apply(e, a);
+  e.ag.need_begin = 0;
+}
+// per-env outputs of rlm_env_step / rlm_agent_update
+__global__ void rlm_step_out_kernel(DevPtrs ptr, double* reward, unsigned char* terminal, double* delta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.n_envs) return;
+  const EnvHdr& e = *(const EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
+  if (reward) reward[b] = e.ag.last_reward;
+  if (terminal) terminal[b] = (e.phase == PH_DONE || (e.phase == PH_RUN && is_terminal(e))) ? 1 : 0;
+  if (delta) delta[b] = e.ag.last_delta;
+}
+cudaError_t rlm_launch_act(const DevPtrs& ptr, const DynParams& D, int n_envs, int* actions, cudaStream_t st) {
+  rlm_act_kernel<<<(n_envs + 63) / 64, 64, 0, st>>>(ptr, D, actions);
+  return cudaGetLastError();
+}
+cudaError_t rlm_launch_apply(const DevPtrs& ptr, const DynParams& D, int n_envs, const int* actions, cudaStream_t st) {
+  rlm_apply_kernel<<<(n_envs + 63) / 64, 64, 0, st>>>(ptr, D, actions);
+  return cudaGetLastError();
+}
+cudaError_t rlm_launch_step_out(const DevPtrs& ptr, int n_envs, double* reward, unsigned char* terminal, double* delta, cudaStream_t st) {
+  rlm_step_out_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(ptr, reward, terminal, delta);
+  return cudaGetLastError();
 }
 
 __device__ __noinline__ void flow_next_dev(rlm_flow_state* s, rlm_tick_msg* m) {
@@ -316,8 +409,8 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
   if (b < (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) {
     EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
     const int ph = g->phase;
-    const int nb = g->ag.need_begin;
-    if (ph != PH_DONE && (!only_begin || nb)) {
+    const int nb = D.hold ? 0 : g->ag.need_begin;
+    if (ph != PH_DONE && (!only_begin || nb) && !(D.hold && env_on_hold(*g))) {
       EnvHdr e = *g;  // thread-local copy: local memory is lane-interleaved == SoA across the warp
       double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
       if (nb) {
@@ -348,6 +441,12 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
       errs = (unsigned)(e.err | e.ag.err);
       *g = e;
     }
+  }
+  {
+    const bool still = b < (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs) && ready < 0 && !only_begin &&
+                       ((EnvHdr*)(ptr.env + (size_t)b * P.env_stride))->phase != PH_DONE && !env_on_hold(*(EnvHdr*)(ptr.env + (size_t)b * P.env_stride));
+    const unsigned rm = __ballot_sync(FULL, D.hold && still);
+    if (rm && lane == 0) atomicAdd(&ptr.counters[5], (unsigned long long)__popc(rm));
   }
   // ready list: one atomic per warp
   const unsigned m = __ballot_sync(FULL, ready >= 0);
@@ -533,6 +632,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   envw_stage_in(&e, g, lane);
   __syncwarp();
   if (e.phase == PH_DONE) return;
+  if (D.hold && env_on_hold(e)) return;
   int ready = -1;
   unsigned ticked = 0;
   if (e.ag.need_begin) {
@@ -545,6 +645,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   if (!only_begin) KLOG_END(0);
   if (lane == 0) {
     if (ready >= 0) ptr.ready[atomicAdd(&ptr.ready_count[tslot], 1)] = env;
+    if (D.hold && ready < 0 && e.phase != PH_DONE) atomicAdd(&ptr.counters[5], 1ull);  // still inside its step
     if (ticked) atomicAdd(&ptr.counters[0], 1ull);
     const unsigned errs = (unsigned)(e.err | e.ag.err);
     if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);

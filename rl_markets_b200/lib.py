@@ -17,7 +17,7 @@ EXPORTS = [
     "rlm_load_ticks", "rlm_run_ticks", "rlm_sync", "rlm_get_counters", "rlm_get_stats", "rlm_get_state",
     "rlm_get_reward", "rlm_get_actions", "rlm_get_rho", "rlm_get_occupancy", "rlm_copy_theta", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
     "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_shared_tick_accumulate", "rlm_apply_dtheta",
-    "rlm_set_stream", "rlm_set_profiling", "rlm_get_kernel_times",
+    "rlm_set_stream", "rlm_set_profiling", "rlm_get_kernel_times", "rlm_act", "rlm_env_step", "rlm_agent_update",
     "rlm_flow_generate", "rlm_test_to_ticks", "rlm_test_to_price", "rlm_test_tiles", "rlm_test_order",
     "rlm_test_rolling_mean",
 ]
@@ -69,6 +69,9 @@ def load():
     L.rlm_device_ptrs.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_void_p), P(C.c_int64)]
     L.rlm_apply_dtheta.argtypes = [C.c_void_p]
     L.rlm_shared_tick_accumulate.argtypes = [C.c_void_p]
+    L.rlm_act.argtypes = [C.c_void_p, P(C.c_int32)]
+    L.rlm_env_step.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_double), P(C.c_uint8)]
+    L.rlm_agent_update.argtypes = [C.c_void_p, P(C.c_double)]
     L.rlm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.rlm_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     L.rlm_get_kernel_times.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int64)]
@@ -147,6 +150,7 @@ class BatchedMarket:
 
     def set_stream(self, cuda_stream_ptr):
         check(self.L.rlm_set_stream(self.h, cuda_stream_ptr))
+        self._stream_ptr = cuda_stream_ptr
 
     def counters(self):
         c = abi.Counters()
@@ -208,6 +212,26 @@ class BatchedMarket:
         a, b, na, nb = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
         check(self.L.rlm_get_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(na), C.byref(nb)))
         return {"env_ms": a.value, "agent_ms": b.value, "env_launches": na.value, "agent_launches": nb.value}
+
+    # ---- split surface: Environment::step / Agent::update (include/rlm.h)
+    def act(self):
+        """Agent::action for every env at a decision point (-1 elsewhere)."""
+        out = (C.c_int32 * self.cfg.n_envs)()
+        check(self.L.rlm_act(self.h, out))
+        return out
+
+    def env_step(self, actions=None):
+        """Base::performAction + getReward: one learner step's worth of ticks per env.  Returns (rewards, terminal)."""
+        n = self.cfg.n_envs
+        rew, term = (C.c_double * n)(), (C.c_uint8 * n)()
+        check(self.L.rlm_env_step(self.h, actions, rew, term))
+        return rew, term
+
+    def agent_update(self):
+        """State::newState + Agent::HandleTransition for the envs whose step ended; returns the TD errors."""
+        out = (C.c_double * self.cfg.n_envs)()
+        check(self.L.rlm_agent_update(self.h, out))
+        return out
 
     # ---- shared policy (cfg.shared_policy = 1), SURVEY.md section 8e
     def shared_tick_accumulate(self):

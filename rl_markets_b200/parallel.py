@@ -32,16 +32,36 @@ def shared_policy_tick(accumulate, dtheta, apply, dist=None):
 
 
 def run_shared_policy(market, n_ticks, dist=None):
-    """market: rl_markets_b200.lib.BatchedMarket created with shared_policy=True."""
+    """market: rl_markets_b200.lib.BatchedMarket created with shared_policy=True.
+
+    Device-ordered: the handle is put on torch's CURRENT stream, so per tick the accumulate kernels, the NCCL all-reduce
+    of dtheta and the apply kernels are ordered by the stream itself -- the host enqueues all n_ticks ticks without
+    waiting for the device once (torch's NCCL work.wait() blocks the stream, not the host)."""
     dth = market.dtheta_tensor() if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
     if dth is None:
         market.run_ticks(n_ticks)
         return
     import torch
+    caller = torch.cuda.current_stream()
+    if caller.cuda_stream == 0:
+        # the legacy default stream cannot be handed to the library (0 means "your own stream" in rlm_set_stream):
+        # run the ticks on a side stream that is ordered after, and joined back into, the caller's stream
+        side = getattr(market, "_side_stream", None)
+        if side is None:
+            side = market._side_stream = torch.cuda.Stream()
+        side.wait_stream(caller)
+        with torch.cuda.stream(side):
+            _shared_ticks_on_current_stream(market, n_ticks, dist, dth, torch)
+        caller.wait_stream(side)
+    else:
+        _shared_ticks_on_current_stream(market, n_ticks, dist, dth, torch)
+
+
+def _shared_ticks_on_current_stream(market, n_ticks, dist, dth, torch):
+    cur = torch.cuda.current_stream().cuda_stream
+    if getattr(market, "_stream_ptr", None) != cur:
+        market.set_stream(cur)
     for _ in range(n_ticks):
         market.shared_tick_accumulate()
-        # the library runs on its own stream: order the collective after it
-        market.sync()
         dist.all_reduce(dth, op=dist.ReduceOp.SUM)
-        torch.cuda.current_stream().synchronize()
         market.apply_dtheta()

@@ -54,3 +54,61 @@ def test_shared_policy_matches_batch_oracle(rlm, oracle, algo):
     assert np.count_nonzero(ref) > 100
     L.lobo_batch_destroy(b)
     m.close()
+
+
+def test_two_replicas_of_a_shared_policy_match_the_batch_oracle(rlm, oracle):
+    """What two ranks do, in one process: two handles own the two halves of the batch and their own replica of theta;
+    each tick both accumulate, the two dtheta buffers are summed into both (the all-reduce), both apply.  Weights written
+    only by the OTHER replica's envs must be visible to this replica's evaluations (round 1 filtered its gathers through
+    a rank-local occupancy bitmap)."""
+    import torch
+    from test_shared_policy_cpu import _oracle_batch
+    n_envs, n_ticks, M, cap = 16, 300, 4096, 250
+    y = config.example_dict(**{"learning.memory_size": M, "learning.algorithm": "q_learn"})
+    halves = []
+    for r in range(2):
+        c = config.from_dict(y, n_envs=n_envs // 2, env_index0=r * (n_envs // 2), shared_policy=True, flow_seed=33)
+        c.record_envs, c.record_cap = n_envs // 2, cap
+        halves.append(rlm.BatchedMarket(c))
+    stream = torch.cuda.Stream()  # (a real stream: 0 would mean "the handle's own stream" to rlm_set_stream)
+    dths = []
+    for m in halves:
+        m.set_stream(stream.cuda_stream)
+        dths.append(m.dtheta_tensor())
+    with torch.cuda.stream(stream):
+        for t in range(n_ticks):
+            for m in halves:
+                m.shared_tick_accumulate()
+            total = dths[0] + dths[1]
+            dths[0].copy_(total)
+            dths[1].copy_(total)
+            for m in halves:
+                m.apply_dtheta()
+    for m in halves:
+        m.sync()
+    cfg = config.from_dict(y, n_envs=n_envs, shared_policy=True, flow_seed=33)
+    L, b = _oracle_batch(cfg)
+    streams = [rlm.flow_generate(cfg.flow, i, 0, n_ticks) for i in range(n_envs)]
+    recs = (abi.StepRecord * (n_envs * cap))()
+    cnt = (C.c_int32 * n_envs)()
+    msgs = (abi.TickMsg * n_envs)()
+    for t in range(n_ticks):
+        for i in range(n_envs):
+            msgs[i] = streams[i][t]
+        L.lobo_batch_accumulate(b, msgs, C.addressof(recs), C.addressof(cnt), cap)
+        L.lobo_batch_apply(b)
+    for e in range(n_envs):
+        got, _keep = halves[e // (n_envs // 2)].records(e % (n_envs // 2))
+        assert len(got) == cnt[e] > 20, (e, len(got), cnt[e])
+        for i, r in enumerate(got):
+            o = recs[e * cap + i]
+            for f in INT_FIELDS:
+                assert getattr(r, f) == getattr(o, f), (e, i, f)
+            assert abs(r.delta - o.delta) <= 1e-5 * max(abs(r.delta), abs(o.delta), 1e-12), (e, i, r.delta, o.delta)
+    ref = np.ctypeslib.as_array(L.lobo_batch_theta(b, 0), shape=(M,))
+    for m in halves:
+        np.testing.assert_allclose(np.frombuffer(m.theta(0, 0), dtype=np.float64), ref, rtol=1e-5, atol=1e-12)
+    assert bytes(halves[0].theta(0, 0)) == bytes(halves[1].theta(0, 0))  # replicas stay bitwise identical
+    L.lobo_batch_destroy(b)
+    for m in halves:
+        m.close()
