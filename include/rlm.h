@@ -246,6 +246,16 @@ int rlm_get_kernel_times(rlm_handle h, double* env_ms, double* agent_ms, int64_t
 /* run on a caller-provided CUDA stream (cudaStream_t as void*); 0 = the handle's own stream */
 int rlm_set_stream(rlm_handle h, void* cuda_stream);
 
+/* Real-data ingestion (host code, no GPU needed): a reference-format CSV pair -- market depth
+ * (date,HH:MM:SS.mmm,AP1..5,AV1..5,BP1..5,BV1..5) and time-and-sales (date,time,price,size) -- becomes the packed message
+ * stream rlm_load_ticks takes, with exactly the row filtering, print aggregation and row grouping of the reference's
+ * data layer (data::basic::MarketDepth / TimeAndSales src/data/basic.cpp:20-202, Streamer::LoadUntil
+ * src/data/streamer.cpp:57-81, Intraday::UpdateBookProfiles src/environment/intraday.cpp:274-313): depth rows that
+ * share a timestamp or follow an invalid book state are flagged RLM_TICK_PARTIAL, ticks with more than RLM_N_TX_MAX
+ * distinct print prices lead with RLM_TICK_TX_MORE messages (include/rlm_flow.h).  Call with out == NULL to size the
+ * buffer: *n_msgs = messages, *n_ticks = market ticks (NextState calls) they make up. */
+int rlm_ingest_csv(const char* md_path, const char* tas_path, rlm_tick_msg* out, int64_t cap, int64_t* n_msgs, int64_t* n_ticks);
+
 /* host-side synthetic flow (same integer process as the in-kernel generator) */
 int rlm_flow_generate(const rlm_flow_params* p, int64_t env_index, int64_t first_tick, int32_t n_ticks,
                       rlm_tick_msg* out);

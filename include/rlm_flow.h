@@ -47,8 +47,21 @@ typedef struct rlm_tick_msg {
   int32_t n_tx;               /* 0..RLM_N_TX_MAX                 */
   int32_t time_ms;            /* ms since midnight of the depth row (utilities/time.h:28-39) */
   int32_t date;               /* yyyymmdd                        */
-  int32_t flags;              /* reserved, 0                     */
+  int32_t flags;              /* RLM_TICK_* below; 0 for one depth row = one tick (the synthetic flow) */
 } rlm_tick_msg;
+
+/* Real data does not always give one depth row per tick (rlm_ingest_csv sets these; the generator never does):
+ *   RLM_TICK_PARTIAL  further depth rows of the SAME tick follow.  Intraday::UpdateBookProfiles keeps applying rows --
+ *                     without stashing the book again and with the same prints -- while the next row shares the
+ *                     timestamp (Streamer::WillTimeChange, src/environment/intraday.cpp:281-298)
+ *                     or the book state is invalid (BookUtils::IsValidState, :300-309).  The tick completes with the
+ *                     first following message that does not carry the flag.
+ *   RLM_TICK_TX_MORE  the message carries no depth row, only up to RLM_N_TX_MAX further aggregated prints (ascending
+ *                     price, all below the prices that follow) of the tick that the next depth row opens: a
+ *                     TimeAndSalesRecord with more than RLM_N_TX_MAX distinct prices (at most RLM_TX_CAP in total). */
+#define RLM_TICK_PARTIAL 1
+#define RLM_TICK_TX_MORE 2
+#define RLM_TX_CAP 16
 
 /* Generator parameters.  All integer. */
 typedef struct rlm_flow_params {

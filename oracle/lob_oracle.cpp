@@ -310,8 +310,8 @@ inline double pkey(double p) { return std::rint(p * 10000u); }  // utilities/com
 
 struct Tx {  // data::TimeAndSalesRecord::transactions (records.h:32), ascending FloatComparator order
   int n = 0;
-  double px[RLM_N_TX_MAX];
-  long vol[RLM_N_TX_MAX];
+  double px[RLM_TX_CAP];
+  long vol[RLM_TX_CAP];
   long find(double price) const {  // map::find by comparator key
     double k = pkey(price);
     for (int i = 0; i < n; ++i) if (pkey(px[i]) == k) return vol[i];
@@ -850,23 +850,39 @@ struct lobo_env {
     if (position > 0) tick_stats.t_long++; else if (position < 0) tick_stats.t_short++;
   }
 
-  static Tx make_tx(const rlm_tick_msg& m) {
-    Tx t;
-    t.n = m.n_tx;
-    for (int i = 0; i < m.n_tx; ++i) { t.px[i] = (double)m.tx_px[i]; t.vol[i] = m.tx_vol[i]; }
-    return t;
+  // One tick of the packed stream = [RLM_TICK_TX_MORE messages] + [depth rows flagged RLM_TICK_PARTIAL] + one last depth
+  // row (include/rlm_flow.h).  The synthetic flow has exactly one message per tick.
+  struct TickGroup { Tx tx; std::vector<const rlm_tick_msg*> rows; };
+  // collects the group that starts at msgs[i]; false (i untouched) if the buffer ends inside it
+  static bool take_group(const rlm_tick_msg* msgs, int64_t n, int64_t& i, TickGroup& g) {
+    g.tx.n = 0; g.rows.clear();
+    int64_t k = i;
+    auto add_tx = [&](const rlm_tick_msg& m) {
+      for (int t = 0; t < m.n_tx && g.tx.n < RLM_TX_CAP; ++t) { g.tx.px[g.tx.n] = (double)m.tx_px[t]; g.tx.vol[g.tx.n] = m.tx_vol[t]; g.tx.n++; }
+    };
+    while (k < n && (msgs[k].flags & RLM_TICK_TX_MORE)) add_tx(msgs[k++]);
+    bool first = true;
+    while (k < n) {
+      const rlm_tick_msg& m = msgs[k++];
+      if (first) { add_tx(m); first = false; }
+      g.rows.push_back(&m);
+      if (!(m.flags & RLM_TICK_PARTIAL)) { i = k; return true; }
+    }
+    return false;
   }
 
-  // Intraday::UpdateBookProfiles intraday.cpp:274-313 for ONE depth row (the stream contract:
-  // one message = one row with a new timestamp)
-  void UpdateBookProfiles(const rlm_tick_msg& m, const Tx& tx) {
+  // Intraday::UpdateBookProfiles intraday.cpp:274-313: one StashState, then every depth row of the tick
+  void UpdateBookProfiles(const TickGroup& g, const Tx& tx) {
     ask.StashState(); bid.StashState();
-    last_date = market.date;
-    market.date = m.date; market.time = m.time_ms;
-    double ap[RLM_DEPTH], bp[RLM_DEPTH]; long av[RLM_DEPTH], bv[RLM_DEPTH];
-    for (int l = 0; l < RLM_DEPTH; ++l) { ap[l] = (double)m.ask_px[l]; bp[l] = (double)m.bid_px[l]; av[l] = m.ask_vol[l]; bv[l] = m.bid_vol[l]; }
-    ask.ApplyChanges(ap, av, tx);
-    bid.ApplyChanges(bp, bv, tx);
+    for (const rlm_tick_msg* pm : g.rows) {
+      const rlm_tick_msg& m = *pm;
+      last_date = market.date;
+      market.date = m.date; market.time = m.time_ms;
+      double ap[RLM_DEPTH], bp[RLM_DEPTH]; long av[RLM_DEPTH], bv[RLM_DEPTH];
+      for (int l = 0; l < RLM_DEPTH; ++l) { ap[l] = (double)m.ask_px[l]; bp[l] = (double)m.bid_px[l]; av[l] = m.ask_vol[l]; bv[l] = m.bid_vol[l]; }
+      ask.ApplyChanges(ap, av, tx);
+      bid.ApplyChanges(bp, bv, tx);
+    }
     if (!is_valid_state(ask, bid)) invalid_states++;
   }
 
@@ -875,13 +891,13 @@ struct lobo_env {
   }
 
   // Intraday::NextState intraday.cpp:224-272
-  void NextState(const rlm_tick_msg& m) {
-    Tx tx = make_tx(m);
+  void NextState(const TickGroup& g) {
+    const Tx& tx = g.tx;
     double mp = m_midprice(ask, bid);
     long au0, bu0; double au1, au2, bu1, bu2;
     ask.ApplyTransactions(tx, mp, au0, au1, au2);
     bid.ApplyTransactions(tx, mp, bu0, bu1, bu2);
-    UpdateBookProfiles(m, tx);
+    UpdateBookProfiles(g, tx);
     long as0; double as1, as2;
     adverse_selection(ask, bid, as0, as1, as2);
     pnl_step += au1 + bu1 + as1;
@@ -1149,7 +1165,7 @@ struct lobo_env {
   }
 
   // one tick of the do-while of base.cpp:285-305; returns true when the loop exits
-  bool run_tick(const rlm_tick_msg& m) {
+  bool run_tick(const TickGroup& m) {
     pnl_step = 0.0;
     NextState(m);
     double mpm = m_midprice_move(ask, bid);
@@ -1226,8 +1242,11 @@ struct lobo_env {
 
   // shared-policy batch: one tick; returns true when a learner step ended and begin_step() is pending
   // (it must run only after the batch applied theta += dtheta)
-  bool tick_deferred(const rlm_tick_msg& m, rlm_step_record* rec) {
+  bool tick_deferred(const rlm_tick_msg& one, rlm_step_record* rec) {
     if (phase == PH_DONE) return false;
+    TickGroup m;
+    int64_t at = 0;
+    if (!take_group(&one, 1, at, m)) throw std::runtime_error("the shared-policy batch takes one-message ticks");
     if (phase == PH_PREOPEN) {
       Tx none;
       UpdateBookProfiles(m, none);
@@ -1251,9 +1270,10 @@ struct lobo_env {
   int64_t run(const rlm_tick_msg* msgs, int64_t n_msgs, int64_t max_steps, rlm_step_record* recs, int64_t rec_cap,
               int64_t* n_consumed) {
     int64_t steps = 0, i = 0, nrec = 0;
+    TickGroup m;
     while (i < n_msgs && phase != PH_DONE) {
       if (max_steps >= 0 && steps >= max_steps) break;
-      const rlm_tick_msg& m = msgs[i++];
+      if (!take_group(msgs, n_msgs, i, m)) break;  // the buffer ends inside a multi-message tick
       if (phase == PH_PREOPEN) {  // intraday.cpp:111-116
         Tx none;
         UpdateBookProfiles(m, none);

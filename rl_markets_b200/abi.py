@@ -23,6 +23,7 @@ VAR = {"pos": 0, "spd": 1, "mpm": 2, "imb": 3, "svl": 4, "vol": 5, "rsi": 6, "vw
 TP_YAML = {"midprice": 0, "microprice": 1, "vwap": 2, "book": 3}
 MODE_TRAIN, MODE_BACKTEST = 0, 1
 SOURCE_GENERATOR, SOURCE_STREAM = 0, 1
+TICK_PARTIAL, TICK_TX_MORE = 1, 2  # rlm_tick_msg.flags (include/rlm_flow.h)
 
 RLM_OK = 0
 RLM_ERR_INVALID_ARGUMENT = -1

@@ -23,6 +23,7 @@
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int rlm_set_error_(int code, const std::string& msg) { return fail(code, msg); }  // for the host-only translation units
 #define CK(expr)                                                                                      \
   do {                                                                                                \
     cudaError_t _e = (expr);                                                                          \

@@ -176,13 +176,16 @@ __device__ __noinline__ void side_update_order(SideD& s, long long transaction_v
   }
 }
 
-// Book::StashState + Book::ApplyChanges for one depth row (book.cpp:50-55,63-99).
-// px/vol: the side's 5 levels, best first (the stream contract; rlm_load_ticks validates order).
-__device__ __noinline__ void side_apply_changes(SideD& s, const float* px, const int* vol, const rlm_tick_msg& m, int* err) {
+// Book::StashState (book.cpp:50-55)
+__device__ __forceinline__ void side_stash(SideD& s) {
 #pragma unroll
   for (int l = 0; l < RLM_DEPTH; ++l) { s.last_px[l] = s.px[l]; s.last_vol[l] = s.vol[l]; }
   s.has_last = s.has_cur;
   s.last_total_vol = s.total_vol;
+}
+// Book::ApplyChanges for one depth row (book.cpp:63-99).  px/vol: the side's 5 levels, best first (the stream contract);
+// tpx/tvol/n_tx: the tick's aggregated prints (the `transactions` map handed through UpdateBookProfiles).
+__device__ __forceinline__ void side_apply_row(SideD& s, const float* px, const int* vol, const float* tpx, const int* tvol, int n_tx, int* err) {
   long long tv = s.total_vol;
 #pragma unroll
   for (int l = 0; l < RLM_DEPTH; ++l) {
@@ -198,27 +201,31 @@ __device__ __noinline__ void side_apply_changes(SideD& s, const float* px, const
     // transactions.find(order price) by comparator key (book.cpp:94-95)
     long long t = 0;
     double k = pkey(s.ord.price);
-    for (int i = 0; i < m.n_tx; ++i)
-      if (pkey((double)m.tx_px[i]) == k) t = m.tx_vol[i];
+    for (int i = 0; i < n_tx; ++i)
+      if (pkey((double)tpx[i]) == k) t = tvol[i];
     side_update_order(s, t);
   }
+}
+// Book::StashState + Book::ApplyChanges for one depth row = one tick (the synthetic flow's contract)
+__device__ __noinline__ void side_apply_changes(SideD& s, const float* px, const int* vol, const rlm_tick_msg& m, int* err) {
+  side_stash(s);
+  side_apply_row(s, px, vol, m.tx_px, m.tx_vol, m.n_tx, err);
 }
 
 struct Fill { long long volume; double proxy, value; };
 
-// AskBook::ApplyTransactions (book.cpp:382-427) / BidBook::ApplyTransactions (:467-510)
+// AskBook::ApplyTransactions (book.cpp:382-427) / BidBook::ApplyTransactions (:467-510) over n aggregated prints
 template <bool IS_ASK>
-__device__ __noinline__ Fill side_apply_transactions(SideD& s, const rlm_tick_msg& m, double ref, bool use_tx) {
+__device__ __forceinline__ Fill side_apply_transactions_n(SideD& s, const float* tpx, const int* tvol, int n, double ref) {
   s.obs_value = 0.0;
   s.obs_volume = 0;
   Fill f; f.volume = 0; f.proxy = 0.0; f.value = 0.0;
   OrderD& o = s.ord;
-  const int n = use_tx ? m.n_tx : 0;
   for (int k = 0; k < n; ++k) {
     const int i = IS_ASK ? k : n - 1 - k;
-    const double tp = (double)m.tx_px[i];
+    const double tp = (double)tpx[i];
     if (IS_ASK ? (tp < ref) : (tp > ref)) continue;
-    long long vol = m.tx_vol[i];
+    long long vol = tvol[i];
     s.obs_value += tp * (double)vol;
     s.obs_volume += vol;
     while (o.live && (IS_ASK ? (o.price <= tp) : (o.price >= tp))) {
@@ -239,6 +246,10 @@ __device__ __noinline__ Fill side_apply_transactions(SideD& s, const rlm_tick_ms
     }
   }
   return f;
+}
+template <bool IS_ASK>
+__device__ __noinline__ Fill side_apply_transactions(SideD& s, const rlm_tick_msg& m, double ref, bool use_tx) {
+  return side_apply_transactions_n<IS_ASK>(s, m.tx_px, m.tx_vol, use_tx ? m.n_tx : 0, ref);
 }
 
 // AskBook/BidBook::WalkTheBook (book.cpp:429-456,512-539)
@@ -492,6 +503,64 @@ __device__ __noinline__ void next_state_warp(EnvHdr& e, const rlm_tick_msg& m, d
     check_valid_state(e);
     next_state_tail(e, fills[0], fills[1], pushv);
   }
+}
+
+// ---------------------------------------------------------------- multi-message ticks (ingested real data)
+// One tick = [RLM_TICK_TX_MORE messages] + [depth rows flagged RLM_TICK_PARTIAL] + one last depth row (rlm_flow.h).
+// needs_multi: this message cannot take the one-row fast path.
+__device__ __forceinline__ bool needs_multi(const EnvHdr& e, const rlm_tick_msg& m) { return (m.flags & 3) != 0 || e.tick_open != 0 || e.txn != 0; }
+__device__ __forceinline__ void tick_tx_append(EnvHdr& e, const rlm_tick_msg& m) {
+  for (int i = 0; i < m.n_tx && i < RLM_N_TX_MAX; ++i) {
+    if (e.txn >= RLM_TX_CAP) { e.err |= ERR_BAD_PRICE; break; }
+    e.tx_px[e.txn] = m.tx_px[i]; e.tx_vol[e.txn] = m.tx_vol[i]; e.txn++;
+  }
+}
+// Intraday::UpdateBookProfiles (intraday.cpp:274-313) one depth row at a time; returns true when the tick's last row is in
+__device__ __noinline__ bool update_book_profiles_multi(EnvHdr& e, const rlm_tick_msg& m, bool with_tx) {
+  if (m.flags & RLM_TICK_TX_MORE) { if (with_tx && !e.tick_open) tick_tx_append(e, m); return false; }
+  if (!e.tick_open) {
+    if (with_tx) tick_tx_append(e, m); else e.txn = 0;
+    side_stash(e.side[0]);
+    side_stash(e.side[1]);
+  }
+  e.last_date = e.date;  // intraday.cpp:286-288, once per row
+  e.date = m.date;
+  e.time_ms = m.time_ms;
+  side_apply_row(e.side[0], m.ask_px, m.ask_vol, e.tx_px, e.tx_vol, e.txn, &e.err);
+  side_apply_row(e.side[1], m.bid_px, m.bid_vol, e.tx_px, e.tx_vol, e.txn, &e.err);
+  if (m.flags & RLM_TICK_PARTIAL) { e.tick_open = 1; return false; }
+  e.tick_open = 0;
+  e.txn = 0;
+  return true;
+}
+// Intraday::NextState (intraday.cpp:224-272) for such a tick, one message at a time, one thread; returns true (and fills
+// pushv) when the tick is complete
+__device__ __noinline__ bool next_state_multi(EnvHdr& e, const rlm_tick_msg& m, double* pushv) {
+  if (m.flags & RLM_TICK_TX_MORE) { if (!e.tick_open) tick_tx_append(e, m); return false; }
+  if (!e.tick_open) {  // first depth row of the tick: the prints meet the book of the previous tick (intraday.cpp:235-237)
+    tick_tx_append(e, m);
+    const double mp = m_midprice(e);
+    const Fill au = side_apply_transactions_n<true>(e.side[0], e.tx_px, e.tx_vol, e.txn, mp);
+    const Fill bu = side_apply_transactions_n<false>(e.side[1], e.tx_px, e.tx_vol, e.txn, mp);
+    e.tick_au.volume = au.volume; e.tick_au.proxy = au.proxy; e.tick_au.value = au.value;
+    e.tick_bu.volume = bu.volume; e.tick_bu.proxy = bu.proxy; e.tick_bu.value = bu.value;
+    side_stash(e.side[0]);
+    side_stash(e.side[1]);
+  }
+  e.last_date = e.date;
+  e.date = m.date;
+  e.time_ms = m.time_ms;
+  side_apply_row(e.side[0], m.ask_px, m.ask_vol, e.tx_px, e.tx_vol, e.txn, &e.err);
+  side_apply_row(e.side[1], m.bid_px, m.bid_vol, e.tx_px, e.tx_vol, e.txn, &e.err);
+  if (m.flags & RLM_TICK_PARTIAL) { e.tick_open = 1; return false; }
+  e.tick_open = 0;
+  e.txn = 0;
+  check_valid_state(e);
+  Fill au, bu;
+  au.volume = e.tick_au.volume; au.proxy = e.tick_au.proxy; au.value = e.tick_au.value;
+  bu.volume = e.tick_bu.volume; bu.proxy = e.tick_bu.proxy; bu.value = e.tick_bu.value;
+  next_state_tail(e, au, bu, pushv);
+  return true;
 }
 
 // ulb() of include/utilities/maths.h:4-8 = std::max(std::min(val, ub), lb): a NaN `val` comes back as NaN (both

@@ -347,7 +347,12 @@ __device__ __noinline__ void flow_next_warp(rlm_flow_state* s, rlm_tick_msg* m, 
 // ended (state variables + reward are in e.ag), 1 = warm-up ended (Intraday::Initialise done).
 __device__ __noinline__ int env_tick(EnvHdr& e, double* ring, const rlm_tick_msg& msg, int backtest) {
   const int phase = e.phase;
+  const bool multi = needs_multi(e, msg);  // ingested real data: this tick spans several messages (rlm_flow.h)
   if (phase == PH_PREOPEN) {  // intraday.cpp:111-116: rows before the open only update the book
+    if (multi) {
+      if (update_book_profiles_multi(e, msg, false) && market_is_open(e)) e.phase = PH_WARMUP;
+      return -1;
+    }
     rlm_tick_msg none = msg;
     none.n_tx = 0;
     update_book_profiles(e, none);
@@ -358,7 +363,8 @@ __device__ __noinline__ int env_tick(EnvHdr& e, double* ring, const rlm_tick_msg
 #pragma unroll
   for (int w = 0; w < RLM_NWIN; ++w) oldv[w] = window_peek(e, ring, w);  // 10 independent loads, consumed after the book logic
   if (phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
-  next_state_scalar(e, msg, pushv);       // Intraday::NextState
+  if (multi) { if (!next_state_multi(e, msg, pushv)) return -2; }  // (message consumed, tick not complete yet)
+  else next_state_scalar(e, msg, pushv);  // Intraday::NextState
 #pragma unroll 1
   for (int w = 0; w < 8; ++w) window_push(e, ring, w, pushv[w], oldv[w]);
   e.tp_val = e.w_mean[W_TP];
@@ -435,7 +441,8 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
         if (have) {
           const int was = e.phase;
           ready = env_tick(e, ring, msg, D.backtest);
-          if (was != PH_PREOPEN) ticked = 1;
+          if (was != PH_PREOPEN && ready != -2) ticked = 1;
+          if (ready == -2) ready = -1;
         }
       }
       errs = (unsigned)(e.err | e.ag.err);
@@ -529,17 +536,32 @@ __device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const D
   if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);  // issued early, consumed after the book logic
   __syncwarp();
   const int phase = e.phase;
+  const bool multi = have && needs_multi(e, msg);  // ingested real data: this tick spans several messages (rlm_flow.h)
+  int complete = 1;
+  if (multi && phase != PH_PREOPEN) {  // lane 0 runs the one-thread version; the tick may not be complete yet
+    if (lane == 0) {
+      if (phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
+      complete = next_state_multi(e, msg, pushv) ? 1 : 0;
+    }
+    complete = __shfl_sync(FULL, complete, 0);
+  }
   if (have && phase == PH_PREOPEN) {  // intraday.cpp:111-116
     if (lane == 0) {
-      msg.n_tx = 0;
-      update_book_profiles(e, msg);
-      if (market_is_open(e)) e.phase = PH_WARMUP;
+      if (multi) {
+        if (update_book_profiles_multi(e, msg, false) && market_is_open(e)) e.phase = PH_WARMUP;
+      } else {
+        msg.n_tx = 0;
+        update_book_profiles(e, msg);
+        if (market_is_open(e)) e.phase = PH_WARMUP;
+      }
     }
-  } else if (have) {
+  } else if (have && complete) {
     ticked += 1;
-    if (lane == 0 && phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
-    __syncwarp();
-    next_state_warp(e, msg, pushv, w.fills, lane);  // Intraday::NextState, ask side on lane 0, bid side on lane 1
+    if (!multi) {
+      if (lane == 0 && phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
+      __syncwarp();
+      next_state_warp(e, msg, pushv, w.fills, lane);  // Intraday::NextState, ask side on lane 0, bid side on lane 1
+    }
     __syncwarp();
     if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
     __syncwarp();
@@ -1424,21 +1446,30 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 2) rlm_fused_kernel(DevPtrs 
     }
     if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);
     __syncwarp();
+    const bool multi = needs_multi(e, msg);
     if (phase == PH_PREOPEN) {  // intraday.cpp:111-116
       if (lane == 0) {
-        msg.n_tx = 0;
-        update_book_profiles(e, msg);
-        if (market_is_open(e)) e.phase = PH_WARMUP;
+        if (multi) {
+          if (update_book_profiles_multi(e, msg, false) && market_is_open(e)) e.phase = PH_WARMUP;
+        } else {
+          msg.n_tx = 0;
+          update_book_profiles(e, msg);
+          if (market_is_open(e)) e.phase = PH_WARMUP;
+        }
       }
       __syncwarp();
       continue;
     }
-    ticked++;
     if (lane == 0) {
       if (phase == PH_RUN) e.pnl_step = 0.0;  // base.cpp:286
-      next_state_scalar(e, msg, pushv);       // Intraday::NextState
+      int done = 1;
+      if (multi) done = next_state_multi(e, msg, pushv) ? 1 : 0;
+      else next_state_scalar(e, msg, pushv);  // Intraday::NextState
+      *flag = done;
     }
     __syncwarp();
+    if (!*flag) { __syncwarp(); continue; }  // (a multi-message tick that is not complete yet)
+    ticked++;
     if (lane < 8) window_push(e, ring, lane, pushv[lane], oldv[lane]);
     __syncwarp();
     if (lane == 0) {
@@ -1606,7 +1637,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 4) rlm_run_kernel(DevPtrs ptr, Dy
         const int was = e.phase;
         const int r = env_tick(e, ring, msg, 0);
         ticks_left--; tick_idx++;
-        if (was != PH_PREOPEN) ticked++;
+        if (was != PH_PREOPEN && r != -2) ticked++;
         if (r >= 0) {
           // publish what the agent warp needs (the whole record for envs with a parity dump)
           if (b < P.record_envs) *g = e; else g->ag = e.ag;

@@ -73,6 +73,8 @@ struct alignas(16) AgentD {
   int pad[2];
 };
 
+struct FillD { long long volume; double proxy, value; };  // what Ask/BidBook::ApplyTransactions returns (book.cpp:382-427)
+
 struct EnvHdr {
   SideD side[2];  // 0 = ask, 1 = bid
   long long position;  // RiskManager::position_
@@ -88,6 +90,12 @@ struct EnvHdr {
   int market_buys, market_sells;
   int ts_total, ts_ask, ts_bid, ts_both, ts_pos, ts_long, ts_short;
   int err;
+  // multi-message ticks of ingested real data (RLM_TICK_PARTIAL / RLM_TICK_TX_MORE, rlm_flow.h): the tick's prints and the
+  // fills of its ApplyTransactions, kept until the last depth row of the tick has been applied
+  int tick_open, txn;
+  float tx_px[RLM_TX_CAP];
+  int tx_vol[RLM_TX_CAP];
+  FillD tick_au, tick_bu;
   rlm_flow_state flow;
   AgentD ag;
 };

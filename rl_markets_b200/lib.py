@@ -17,7 +17,7 @@ EXPORTS = [
     "rlm_load_ticks", "rlm_run_ticks", "rlm_sync", "rlm_get_counters", "rlm_get_stats", "rlm_get_state",
     "rlm_get_reward", "rlm_get_actions", "rlm_get_rho", "rlm_get_occupancy", "rlm_copy_theta", "rlm_handle_terminal", "rlm_go_greedy", "rlm_read_theta",
     "rlm_write_theta", "rlm_read_records", "rlm_device_ptrs", "rlm_shared_tick_accumulate", "rlm_apply_dtheta",
-    "rlm_set_stream", "rlm_set_profiling", "rlm_get_kernel_times", "rlm_act", "rlm_env_step", "rlm_agent_update",
+    "rlm_set_stream", "rlm_set_profiling", "rlm_get_kernel_times", "rlm_act", "rlm_env_step", "rlm_agent_update", "rlm_ingest_csv",
     "rlm_flow_generate", "rlm_test_to_ticks", "rlm_test_to_price", "rlm_test_tiles", "rlm_test_order",
     "rlm_test_rolling_mean",
 ]
@@ -75,6 +75,7 @@ def load():
     L.rlm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.rlm_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     L.rlm_get_kernel_times.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int64)]
+    L.rlm_ingest_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, P(C.c_int64), P(C.c_int64)]
     L.rlm_flow_generate.argtypes = [P(abi.FlowParams), C.c_int64, C.c_int64, C.c_int32, P(abi.TickMsg)]
     L.rlm_test_to_ticks.argtypes = [P(abi.Config), P(C.c_double), C.c_int32, P(C.c_int32)]
     L.rlm_test_to_price.argtypes = [P(abi.Config), P(C.c_int32), C.c_int32, P(C.c_double)]
@@ -95,6 +96,16 @@ def flow_generate(flow_params, env_index, first_tick, n_ticks):
     out = (abi.TickMsg * n_ticks)()
     check(load().rlm_flow_generate(C.byref(flow_params), env_index, first_tick, n_ticks, out))
     return out
+
+
+def ingest_csv(md_path, tas_path):
+    """Reference-format CSV pair -> (ctypes array of TickMsg, number of market ticks); see rlm_ingest_csv in include/rlm.h."""
+    L = load()
+    n, t = C.c_int64(0), C.c_int64(0)
+    check(L.rlm_ingest_csv(md_path.encode(), tas_path.encode(), None, 0, C.byref(n), C.byref(t)))
+    out = (abi.TickMsg * max(n.value, 1))()
+    check(L.rlm_ingest_csv(md_path.encode(), tas_path.encode(), C.addressof(out), n.value, C.byref(n), C.byref(t)))
+    return out, n.value, t.value
 
 
 class BatchedMarket:

@@ -16,7 +16,16 @@ def _all_cases():
 
 def manifest():
     """Single-episode training cases."""
-    return [c for c in _all_cases() if not c.get("backtest") and not c.get("multi_episode")]
+    return [c for c in _all_cases() if not c.get("backtest") and not c.get("multi_episode") and not c.get("ingest")]
+
+
+def ingest_manifest():
+    """Reference runs on CSV pairs with real-data irregularities (tools/messy_csv.py); the pair is committed beside them."""
+    return [c for c in _all_cases() if c.get("ingest")]
+
+
+def ingest_paths(case):
+    return os.path.join(GOLD, case["name"] + "_md.csv"), os.path.join(GOLD, case["name"] + "_tas.csv")
 
 
 def episode_manifest():

@@ -72,16 +72,14 @@ def test_csv_rendering_round_trips(oracle):
 
 
 def test_csv_ingestion_reproduces_the_packed_stream(oracle):
-    """rl_markets_b200.ingest (reference CSV pair -> packed ticks) inverts oracle/_ref/flow_csv, and the
-    oracle fed with the ingested stream behaves like the reference fed with the CSV files."""
-    from rl_markets_b200 import ingest
+    """rlm_ingest_csv (reference CSV pair -> packed ticks, C++ inside librlm.so, no GPU needed) inverts oracle/_ref/flow_csv."""
     cfg = _cfg(seed=17)
     n = 1500
     packed = lib.flow_generate(cfg.flow, 2, 0, n)
     with tempfile.TemporaryDirectory() as d:
         md, tas = os.path.join(d, "a_md_1.csv"), os.path.join(d, "a_tas_1.csv")
         subprocess.check_call([oracle.FLOW_CSV, "--seed", "17", "--env", "2", "--ticks", str(n), "--md", md, "--tas", tas])
-        got = ingest.csv_pair_to_ticks(md, tas)
-    assert len(got) == n
+        got, n_msgs, n_ticks = lib.ingest_csv(md, tas)
+    assert n_msgs == n_ticks == n
     # the first message's prints are dropped by the reference (SkipUntil); the generator emits none there
     assert bytes(got) == bytes(packed)

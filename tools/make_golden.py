@@ -80,6 +80,16 @@ EPISODE_CASES = [
          over={"policy.type": "boltzmann", "policy.tau_init": 0.05, "policy.tau_floor": 0.01, "policy.tau_T": 2}),
 ]
 
+# Real-data shapes: a CSV pair with depth rows that share a timestamp (A21), a crossed book (the reference
+# swallows the next row into the same tick), rows with a zero price (dropped) and bursts of 5..9 distinct print prices;
+# the reference runs on the files, rlm_ingest_csv + the packed stream have to reproduce it.
+INGEST_CASES = [
+    dict(name="ingest_messy_q_learn", algo="q_learn", M=8192, flow_seed=51, env=27, ticks=1300, messy_seed=3,
+         features=["dup", "zero", "cross", "burst"], over={}),
+    dict(name="ingest_messy_sarsa", algo="sarsa", M=8192, flow_seed=53, env=28, ticks=1300, messy_seed=5,
+         features=["dup", "zero", "cross", "burst"], over={}),
+]
+
 # train on one (short) synthetic day until the close, then main.cpp's evaluation phase (GoGreedy, a NEW Intraday,
 # Backtester::RunEpisode) on another one: steps_<name>.bin = training records, steps_<name>_test.bin = evaluation
 BACKTEST_CASES = [
@@ -141,6 +151,30 @@ def main():
                 f.write(bytes(r))
         manifest.append(dict(c, yaml=y, multi_episode=True, t0_ms=t0, n_records=len(ref["records"]), summary=ref["summary"]))
         print(c["name"], len(ref["records"]), "records over", c["episodes"], "episodes")
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import messy_csv
+    for c in INGEST_CASES:
+        y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
+        y_run = json.loads(json.dumps(y))
+        y_run["debug"]["random_seed"] = y["debug"]["random_seed"] + c["env"]
+        md_out, tas_out = os.path.join(GOLD, c["name"] + "_md.csv"), os.path.join(GOLD, c["name"] + "_tas.csv")
+        with tempfile.TemporaryDirectory() as d:
+            md, tas = os.path.join(d, "c_md_1.csv"), os.path.join(d, "c_tas_1.csv")
+            subprocess.check_call([ol.FLOW_CSV, "--seed", str(c["flow_seed"]), "--env", str(c["env"]), "--ticks", str(c["ticks"]),
+                                   "--md", md, "--tas", tas])
+            messy_csv.make_messy(md, tas, md_out, tas_out, seed=c["messy_seed"], features=c["features"])
+            cfgp, dump = os.path.join(d, "cfg.yaml"), os.path.join(d, "steps.bin")
+            ol.write_ref_yaml(cfgp, y_run)
+            out = subprocess.check_output([ol.REF_DRIVER, "--config", cfgp, "--symbol", "AAL.L", "--md", md_out, "--tas", tas_out,
+                                           "--dump", dump, "--steps", "-1"])
+            summary = json.loads(out.decode().strip().splitlines()[-1])
+            raw = open(dump, "rb").read()
+        with open(os.path.join(GOLD, "steps_%s.bin" % c["name"]), "wb") as f:
+            f.write(raw)
+        n = len(raw) // C.sizeof(abi.StepRecord)
+        manifest.append(dict(c, yaml=y, ingest=True, n_records=n, summary=summary))
+        print(c["name"], n, "records from the reference on the messy CSV pair")
     for c in BACKTEST_CASES:
         y = config.example_dict(**{"learning.memory_size": c["M"], "learning.algorithm": c["algo"], **c["over"]})
         seed = y["debug"]["random_seed"] + c["env"]
