@@ -70,6 +70,12 @@ struct rlm_handle_s {
   // tick-synchronous engine: the batch is cut into n_sub sub-batches, each ticking on its own stream, so that the
   // DRAM-bound gather burst of one sub-batch's learner kernel overlaps the issue-bound scalar tick kernel of another
   int n_sub = 1;
+  // CUDA graphs of the tick-synchronous engine (generator source, one stream): one instantiated graph per chunk length,
+  // valid as long as the per-launch parameters it was captured with are unchanged
+  struct TickGraph { int chunk; DynParams d; cudaGraphExec_t exec; };
+  std::vector<TickGraph> graphs;
+  bool use_graphs = true, graph_warm = false;
+  bool staged = false;  // learner: whole-table staging (memory_size * 8 <= 64 KB, independent single-table policies)
   cudaStream_t sub_stream[RLM_MAX_SUB] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[RLM_MAX_SUB] = {};
 };
@@ -248,8 +254,11 @@ static cudaError_t launch_agent_on(rlm_handle_s* h, const DevPtrs& ptr, const Dy
   const int n = d.n_sub > 0 ? d.n_sub : h->cfg.n_envs;  // worst case: every env of the (sub-)batch is ready
   // Q-learning / SARSA / Double-Q training: the one-warp-per-env learner (rlm_learn.cuh).  The R-learning agents' third
   // evaluation and the backtest step stay on the three-warp kernel's EXTRAS instantiation.
-  if (h->agent_variant == 4 && !d.backtest && h->cfg.algorithm < RLM_ALGO_R_LEARN)
+  if (h->agent_variant == 4 && !d.backtest && h->cfg.algorithm < RLM_ALGO_R_LEARN) {
+    // small per-env tables: the whole table is staged in shared memory by one bulk copy per step (rlm_learn_staged_kernel)
+    if (h->staged && stage == 0) return rlm_launch_learn_staged(ptr, d, n, h->cfg.memory_size, tslot, h->n_sms, st);
     return rlm_launch_learn(ptr, d, n, h->hp.is_double, tslot, h->n_sms, stage, st);
+  }
   if (h->agent_variant >= 3) {
     const int full = (d.backtest || h->cfg.algorithm >= RLM_ALGO_R_LEARN) ? 1 : 0;
     return rlm_launch_agent3(ptr, d, n, h->hp.is_double, h->hp.occ_smem_words, tslot, h->n_sms, stage, full, st);
@@ -364,8 +373,17 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
   CK(cudaMalloc(&h->ptr.hsum, (size_t)cfg->n_envs * 3 * 32 * 8));
   h->ready_cap = 256;
   CK(cudaMalloc(&h->ptr.ready_count, (size_t)RLM_MAX_SUB * h->ready_cap * 4));
-  // sub-batches of the tick-synchronous engine (see rlm_handle_s::n_sub): 4 streams from 2048 envs up
-  h->n_sub = (cfg->n_envs >= 2048 && !cfg->shared_policy) ? 4 : 1;
+  // sub-batches of the tick-synchronous engine (see rlm_handle_s::n_sub); RLM_SUBBATCHES overrides
+  h->n_sub = 1;  // (measured on B200: co-resident tick and learner kernels slow each other down as much as they overlap)
+  h->staged = !h->hp.is_double && !cfg->shared_policy && cfg->memory_size * 8 <= 65536 && (cfg->memory_size % 2) == 0;
+  if (const char* s = getenv("RLM_STAGED")) h->staged = h->staged && atoi(s) != 0;
+  // Large batches are throughput-bound: what counts is how many steps an SM keeps in flight.  The one-warp learner holds
+  // 20 KB of shared memory per step (9 per SM); the round-1 three-warp kernel holds 7 KB and 64 registers (10 CTAs = 30
+  // warps per SM) and measures 30 % faster at 65 536 envs (C2), so it takes over above 16 384 envs unless the table is
+  // small enough to be staged whole.
+  if (cfg->n_envs > 16384 && !h->staged) h->agent_variant = 3;
+  if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
+  if (const char* s = getenv("RLM_GRAPHS")) h->use_graphs = atoi(s) != 0;
   if (const char* s = getenv("RLM_SUBBATCHES")) { const int v = atoi(s); if (v >= 1 && v <= RLM_MAX_SUB) h->n_sub = cfg->shared_policy ? 1 : v; }
   if (h->n_sub > 1) {
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -431,6 +449,7 @@ int rlm_destroy(rlm_handle h) {
   cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count); cudaFree(h->ptr.occ); cudaFree(h->ptr.hsum);
   cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
   for (auto e : h->ev) cudaEventDestroy(e);
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int s = 0; s < RLM_MAX_SUB; ++s) {
     if (h->sub_stream[s]) { cudaStreamSynchronize(h->sub_stream[s]); cudaStreamDestroy(h->sub_stream[s]); }
@@ -602,6 +621,39 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
     for (int s = 0; s < S; ++s) CK(cudaStreamWaitEvent(h->sub_stream[s], h->ev_fork, 0));
   }
   int done = 0;
+  // One CUDA graph per chunk instead of 2 * chunk launches: every node's parameters are fixed (the generator source has
+  // no stream offset), so the instantiated graph is reused until alpha / epsilon / the mode change.
+  const bool graphs = h->use_graphs && h->graph_warm && S == 1 && !h->profile && h->cfg.source == RLM_SOURCE_GENERATOR;
+  h->graph_warm = true;  // (the first call launches directly: function attributes are set outside any capture)
+  while (graphs && done < n_ticks) {
+    const int chunk = std::min(n_ticks - done, h->ready_cap);
+    DynParams dt = d;
+    dt.env0 = 0; dt.n_sub = B; dt.sub_idx = 0;
+    rlm_handle_s::TickGraph* tg = nullptr;
+    for (auto& g : h->graphs)
+      if (g.chunk == chunk && memcmp(&g.d, &dt, sizeof(DynParams)) == 0) tg = &g;
+    if (!tg) {
+      if (h->graphs.size() >= 8) { for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec); h->graphs.clear(); }
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t ce = cudaMemsetAsync(h->ptr.ready_count, 0, (size_t)chunk * 4, h->stream);
+      for (int t = 0; t < chunk && ce == cudaSuccess; ++t) {
+        ce = rlm_launch_env(h->ptr, dt, B, t, 0, h->env_variant, h->stream);
+        if (ce == cudaSuccess) ce = launch_agent_on(h, h->ptr, dt, t, 0, h->stream);
+      }
+      cudaError_t ce2 = cudaStreamEndCapture(h->stream, &graph);
+      if (ce != cudaSuccess || ce2 != cudaSuccess) { if (graph) cudaGraphDestroy(graph); CK(ce != cudaSuccess ? ce : ce2); }
+      cudaGraphExec_t exec = nullptr;
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CK(ce);
+      h->graphs.push_back({chunk, dt, exec});
+      tg = &h->graphs.back();
+    }
+    CK(cudaGraphLaunch(tg->exec, h->stream));
+    h->launches += 2 * chunk;
+    done += chunk;
+  }
   while (done < n_ticks) {
     const int chunk = std::min(n_ticks - done, h->ready_cap);
     if (h->profile) {

@@ -333,6 +333,27 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
   }
   __syncwarp();
   LPH(1);
+  if (ag.kind == 0 && stage != 2) {
+    // The trace list (read by the trace pass) and the three words of the Mersenne Twister state the next draw touches are
+    // in HBM since the env's previous step: ask L2 for them now, they arrive under the hashing, the gathers and the sums.
+    const int n_tr = ag.n_traces;
+    const int* tf0 = ptr.trace_f + (size_t)env * P.trace_cap;
+    const float* te0 = ptr.trace_e + (size_t)env * P.trace_cap;
+    if (lane * 32 < n_tr) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(tf0 + lane * 32));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(te0 + lane * 32));
+    }
+    if (P.algorithm != RLM_ALGO_Q_LEARN && lane < 3) {
+      int k = ag.mt_pol_idx; if (k >= 312) k -= 312;
+      int kk = k + (lane == 0 ? 0 : (lane == 1 ? 1 : 156)); if (kk >= 312) kk -= 312;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr.mt_pol + (size_t)env * 312 + kk));
+      if (ptr.mt_agt) {
+        int a = ag.mt_agt_idx; if (a >= 312) a -= 312;
+        int aa = a + (lane == 0 ? 0 : (lane == 1 ? 1 : 156)); if (aa >= 312) aa -= 312;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr.mt_agt + (size_t)env * 312 + aa));
+      }
+    }
+  }
   const size_t pol = P.shared_policy ? 0 : (size_t)env;
   double* theta_a = ptr.theta + pol * (size_t)P.memory_size;
   double* theta_b = DBL ? ptr.theta_b + pol * (size_t)P.memory_size : nullptr;
@@ -619,5 +640,272 @@ cudaError_t rlm_launch_fused2(const DevPtrs& ptr, const DynParams& D, int n_envs
   const int grid = (n_envs + FU2_WARPS - 1) / FU2_WARPS;
   if (is_double) rlm_fused2_kernel<true><<<grid, FU2_WARPS * 32, smem, st>>>(ptr, D);
   else rlm_fused2_kernel<false><<<grid, FU2_WARPS * 32, smem, st>>>(ptr, D);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Learner step with the env's WHOLE weight table staged in shared memory by the bulk-copy engine (TMA, 1-D
+// cp.async.bulk + mbarrier): small per-env tables (memory_size * 8 <= 64 KB: BASELINE.json configs[4], 1M LOBs with
+// M = 4096).  Measured on B200 (tools/ubench/gather.cu): a coalesced 32 KB window streams at 6.6-7.0 TB/s, while the 864
+// random 32-byte sectors the gather form of the step needs inside the same window complete at 2.9 TB/s of sector traffic
+// -- and hold the SM's miss tracking hostage.  Here one elected lane issues ONE bulk copy per step; the hashing, the
+// tile-index table and the from-state's tile table are built while it is in flight; both evaluations, the trace pass
+// and the weight update then run against shared memory: the updated weights are written through to HBM (plain stores of
+// the sums the L2 reduction would have produced), and the second evaluation simply walks the updated table -- no
+// gathers, no reductions, no fence, no patching.  One warp per CTA, one CTA per ready env at a time.
+#define LS_IROW 104  // u16 tile indices per action row (96 used; 16-byte aligned rows)
+__host__ __device__ inline size_t ls_fixed_bytes() { return 16 + LN_AG_BYTES + (size_t)RLM_MAX_ACTIONS * LS_IROW * 2 + 2 * TT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48; }
+__host__ __device__ inline size_t ls_smem_bytes(long long memory_size) { return ((ls_fixed_bytes() + 15) & ~(size_t)15) + (size_t)memory_size * 8; }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// exact-order sum of agent.cpp:117-135 for one action: weights come from the staged table through the index row
+__device__ __forceinline__ double ls_chain(const double* tab, const unsigned short* irow) {
+  const double w0 = P.gw[0], w1 = P.gw[1], w2 = P.gw[2];
+  double acc = 0.0, cur[8], nxt[8];
+  {
+    const uint4 i8 = *(const uint4*)irow;
+    const unsigned short* ii = (const unsigned short*)&i8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = w0 * tab[ii[j]];
+  }
+#pragma unroll 1
+  for (int b = 1; b <= 16; ++b) {
+    const int nb = (b < 16) ? b : 0;
+    const double w = (nb < 4) ? w0 : ((nb < 8) ? w1 : w2);
+    const int col = (nb < 8) ? 8 * nb : 8 * (nb - 4);
+    const uint4 i8 = *(const uint4*)(irow + col);
+    const unsigned short* ii = (const unsigned short*)&i8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nxt[j] = w * tab[ii[j]];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += cur[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+  }
+  return acc;
+}
+__device__ __noinline__ double ls_sums(const double* tab, const unsigned short* idx, int lane) {
+  ASSUME_SHARED(tab); ASSUME_SHARED(idx);
+  return (lane < P.n_actions) ? ls_chain(tab, idx + lane * LS_IROW) : 0.0;
+}
+
+__global__ void __launch_bounds__(32, 5) rlm_learn_staged_kernel(DevPtrs ptr, DynParams D, int tslot) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x;
+  unsigned long long* mbar = (unsigned long long*)smem;
+  AgentD& ag = *(AgentD*)(smem + 16);
+  unsigned short* idx_s = (unsigned short*)(smem + 16 + LN_AG_BYTES);
+  int* tt = (int*)(idx_s + RLM_MAX_ACTIONS * LS_IROW);
+  double* q_pre_a = (double*)(tt + 2 * TT_SLOTS);
+  double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
+  double* dec = q_pre_b + RLM_MAX_ACTIONS;
+  double* tab = (double*)(smem + ((ls_fixed_bytes() + 15) & ~(size_t)15));
+  const unsigned mbar_a = smem_u32(mbar), tab_a = smem_u32(tab);
+  const unsigned table_bytes = (unsigned)(P.memory_size * 8);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  unsigned parity = 0;
+  const int n_ready = ptr.ready_count[tslot];
+  const int A = P.n_actions;
+  const unsigned* rnd = rlm_rndseq_table;
+  unsigned long long steps_done = 0, sum_z = 0;
+  constexpr int N16 = (int)(AG_BYTES / 16);
+#pragma unroll 1
+  for (int idx = blockIdx.x; idx < n_ready; idx += gridDim.x) {
+    const int env = ptr.ready[idx];
+    EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
+    double* theta = ptr.theta + (size_t)env * (size_t)P.memory_size;
+    // every lane is done with the previous env's table and index rows; order those generic-proxy accesses before the
+    // bulk copy's async-proxy writes
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(table_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tab_a), "l"(theta),
+                   "r"(table_bytes), "r"(mbar_a)
+                   : "memory");
+    }
+    {
+      const int4* src = (const int4*)&g->ag;
+      int4* dst = (int4*)&ag;
+      const int4 t0 = __ldcg(src + lane);
+      int4 t1 = make_int4(0, 0, 0, 0);
+      if (lane + 32 < N16) t1 = __ldcg(src + lane + 32);
+      dst[lane] = t0;
+      if (lane + 32 < N16) dst[lane + 32] = t1;
+    }
+    __syncwarp();
+    const int kind = ag.kind;
+    const bool main_step = kind == 0;
+    if (main_step) {  // (see ln_step: the trace list and the generator words, asked for now)
+      const int n_tr = ag.n_traces;
+      if (lane * 32 < n_tr) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr.trace_f + (size_t)env * P.trace_cap + lane * 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr.trace_e + (size_t)env * P.trace_cap + lane * 32));
+      }
+    }
+    // ---- tile indices of the state to evaluate (to-state; first from-state at the end of warm-up), under the copy
+    LnSums h;
+    const bool null_state = (kind == 1) && ag.null_from != 0;
+    if (main_step && ag.hs_valid) {
+      const unsigned long long* hs = ptr.hsum + (size_t)env * 96;
+      h.s[0] = __ldcg(hs + lane); h.s[1] = __ldcg(hs + 32 + lane); h.s[2] = __ldcg(hs + 64 + lane);
+      h.null_state = false;
+    } else {
+      h = ln_hash(rnd, main_step ? ag.to_vars : ag.from_vars, null_state, lane);
+    }
+    if (P.m_pow2) {
+#pragma unroll
+      for (int k = 0; k < 3 * RLM_MAX_ACTIONS; ++k)
+        if ((k % RLM_MAX_ACTIONS) < A) idx_s[(k % RLM_MAX_ACTIONS) * LS_IROW + (k / RLM_MAX_ACTIONS) * 32 + lane] = (unsigned short)ln_tile<true>(h, k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3 * RLM_MAX_ACTIONS; ++k)
+        if ((k % RLM_MAX_ACTIONS) < A) idx_s[(k % RLM_MAX_ACTIONS) * LS_IROW + (k / RLM_MAX_ACTIONS) * 32 + lane] = (unsigned short)ln_tile<false>(h, k);
+    }
+    if (main_step) ln_tt_build(tt, ag, lane);
+    __syncwarp();
+    {  // the table has landed
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbar_a), "r"(parity) : "memory");
+      parity ^= 1u;
+    }
+    double q = ls_sums(tab, idx_s, lane);
+    if (kind == 1) {
+      if (lane < A) { ag.q_from[lane] = q; ag.qb_from[lane] = 0.0; }
+      if (!null_state) ag.from_base0[lane] = mod_m(h.s[0]);
+      if (lane == 0) { ag.need_begin = 1; ag.kind = 2; }
+    } else if (main_step) {
+      if (lane < A) { q_pre_a[lane] = q; q_pre_b[lane] = 0.0; }
+      __syncwarp();
+      float rate;
+      double scaled;
+      if (P.algorithm == RLM_ALGO_Q_LEARN) {
+        ln_td_qlearn(ag, q, q_pre_a, D, lane, rate, scaled);
+      } else {
+        if (lane == 0) td_decision(ag, q_pre_a, q_pre_b, ptr.mt_pol + (size_t)env * 312, nullptr, D, dec);
+        __syncwarp();
+        rate = (float)dec[0];
+        scaled = dec[1];
+      }
+      __syncwarp();
+      // ---- Traces::decay + Traces::update + Agent::updateQ (see ln_trace_pass), weights updated in the staged table
+      int* tf = ptr.trace_f + (size_t)env * P.trace_cap;
+      float* te = ptr.trace_e + (size_t)env * P.trace_cap;
+      const bool null_from = ag.null_from != 0;
+      const int action = ag.cur_action;
+      int w = 0;
+      if (rate != 0.0f) {
+        const int n = ag.n_traces;
+#pragma unroll 1
+        for (int base = 0; base < n; base += 32 * TR_AHEAD) {
+          int fq[TR_AHEAD];
+          float eq[TR_AHEAD];
+#pragma unroll
+          for (int k = 0; k < TR_AHEAD; ++k) {
+            const int i = base + 32 * k + lane;
+            fq[k] = (i < n) ? __ldcg(tf + i) : 0;
+            eq[k] = (i < n) ? __ldcg(te + i) : 0.0f;
+          }
+#pragma unroll
+          for (int k = 0; k < TR_AHEAD; ++k) {
+            if (base + 32 * k < n) {
+              const int i = base + 32 * k + lane;
+              const int f = fq[k];
+              const float ev = eq[k] * rate;
+              bool keep = (i < n) && !(ev < 0.01f);
+              if (keep) keep = (null_from ? (f == 0 ? A - 1 : -1) : tt_last_writer(tt, f)) < 0;
+              const unsigned mask = __ballot_sync(FULL, keep);
+              const int pos = w + __popc(mask & ((1u << lane) - 1u));
+              if (keep) {
+                __stcg(tf + pos, f);
+                __stcg(te + pos, ev);
+                const double nv = tab[f] + scaled * (double)ev;  // the addition the L2 reduction performs
+                tab[f] = nv;
+                __stcg(theta + f, nv);
+              }
+              w += __popc(mask);
+            }
+          }
+        }
+      }
+      {
+        int f = 0;
+        if (!null_from) {
+          f = ag.from_base0[lane] + P.ra_m[action];
+          if (f >= (int)P.memory_size) f -= (int)P.memory_size;
+        }
+        bool add = null_from ? (action == A - 1) : (tt_last_writer(tt, f) == action);
+        const unsigned same = __match_any_sync(FULL, f);
+        add = add && ((__ffs(same) - 1) == lane);
+        const unsigned mask = __ballot_sync(FULL, add);
+        const int pos = w + __popc(mask & ((1u << lane) - 1u));
+        int total = w + __popc(mask);
+        if (total > P.trace_cap) {
+          if (lane == 0) ag.err |= ERR_TRACE_OVERFLOW;
+          add = add && (pos < P.trace_cap);
+          total = P.trace_cap;
+        }
+        if (add) {
+          __stcg(tf + pos, f);
+          __stcg(te + pos, 1.0f);
+          const double nv = tab[f] + scaled * (double)1.0f;
+          tab[f] = nv;
+          __stcg(theta + f, nv);
+        }
+        w = total;
+      }
+      __syncwarp();
+      if (lane == 0) { ag.n_traces = w; ag.sum_traces += w; ag.hs_valid = 0; }
+      sum_z += (lane == 0) ? (unsigned long long)w : 0ull;
+      if (env < P.record_envs) { __threadfence(); emit_record_ool(ptr, g, env, ag, theta, ag.to_vars, lane); }
+      // the to-state becomes the from-state; Q(from, .) under the UPDATED table (serial.cpp:55,60)
+      if (lane < RLM_N_STATE_MAX + 3) { ag.prev_vars[lane] = ag.from_vars[lane]; ag.from_vars[lane] = ag.to_vars[lane]; }
+      ag.from_base0[lane] = mod_m(h.s[0]);
+      if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
+      steps_done++;
+      __syncwarp();
+      q = ls_sums(tab, idx_s, lane);
+      if (lane < A) { ag.q_from[lane] = q; ag.qb_from[lane] = 0.0; }
+    }
+    __syncwarp();
+    {
+      int4* dst = (int4*)&g->ag;
+      const int4* src = (const int4*)&ag;
+      __stcg(dst + lane, src[lane]);
+      if (lane + 32 < N16) __stcg(dst + lane + 32, src[lane + 32]);
+    }
+  }
+  if (lane == 0 && (steps_done | sum_z)) {
+    atomicAdd(&ptr.counters[1], steps_done);
+    atomicAdd(&ptr.counters[2], sum_z);
+  }
+}
+
+// staged form: independent policies, one table per env of at most 64 KB with 16-bit tile indices
+__host__ inline bool rlm_learn_staged_ok(long long memory_size, int is_double, int shared_policy) {
+  return !is_double && !shared_policy && memory_size * 8 <= 65536 && memory_size <= 65536 && (memory_size % 2) == 0;
+}
+cudaError_t rlm_launch_learn_staged(const DevPtrs& ptr, const DynParams& D, int n_envs, long long memory_size, int tslot, int n_sms, cudaStream_t st) {
+  const size_t smem = ls_smem_bytes(memory_size);
+  static size_t attr_smem = 0;
+  static int per_sm = 1;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(rlm_learn_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(rlm_learn_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int n = 0;
+    per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rlm_learn_staged_kernel, 32, smem) == cudaSuccess && n > 0) ? n : 1;
+    attr_smem = smem;
+  }
+  int grid = n_envs;
+  const int cap = n_sms * per_sm;
+  if (grid > cap) grid = cap;
+  rlm_learn_staged_kernel<<<grid, 32, smem, st>>>(ptr, D, tslot);
   return cudaGetLastError();
 }

@@ -23,7 +23,7 @@ m.run_ticks(64); m.sync()
 buf = (C.c_ulonglong * (256 * 8 * 2 * 2))()
 assert L.rlm_debug_klog(buf, 0) == 0
 a = np.frombuffer(buf, dtype=np.uint64).reshape(256, 8, 2, 2).astype(np.int64)
-S = int(os.environ.get("RLM_SUBBATCHES", "4"))
+S = int(os.environ.get("RLM_SUBBATCHES", "1"))
 t0 = min(a[t, s, 0, 0] for t in range(64) for s in range(S) if a[t, s, 0, 1] > 0)
 print("sub-batches %d; times in us since the first env kernel of the call" % S)
 for t in list(range(20, 24)):
