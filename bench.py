@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--e2e-distinct", type=int, default=0, help="0 = every env gets its own host-generated stream")
     ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-ticks", type=int, default=400000)
+    ap.add_argument("--cpu-ticks", type=int, default=1200000)
     ap.add_argument("--ref-ticks", type=int, default=100000)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -368,6 +368,7 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
 #ifdef RLM_TIMING
   if (const char* s = getenv("RLM_DEBUG_FLAGS")) h->dyn.debug_flags = atoi(s);
 #endif
+  if (const char* s = getenv("RLM_ENV_HASH")) h->dyn.env_hash = atoi(s) != 0;
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaMalloc(&h->ptr.ready, (size_t)cfg->n_envs * 4));
   CK(cudaMalloc(&h->ptr.hsum, (size_t)cfg->n_envs * 3 * 32 * 8));

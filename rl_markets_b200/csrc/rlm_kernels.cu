@@ -417,7 +417,19 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
     const int ph = g->phase;
     const int nb = D.hold ? 0 : g->ag.need_begin;
     if (ph != PH_DONE && (!only_begin || nb) && !(D.hold && env_on_hold(*g))) {
-      EnvHdr e = *g;  // thread-local copy: local memory is lane-interleaved == SoA across the warp
+      // thread-local copy: local memory is lane-interleaved == SoA across the warp.  The agent block (the last 700 of the
+      // record's 2 000 bytes) only travels when this tick touches it: an action selection now, or a step end below.
+      EnvHdr e;
+      constexpr int HOT16 = (int)(offsetof(EnvHdr, ag) / 16), ALL16 = (int)(sizeof(EnvHdr) / 16);
+      static_assert(offsetof(EnvHdr, ag) % 16 == 0 && sizeof(EnvHdr) % 16 == 0, "16-byte copies of the two halves of the record");
+      bool ag_in = nb || D.hold || D.backtest;
+      {
+        const int4* src = (const int4*)g;
+        int4* dst = (int4*)&e;
+        for (int i = 0; i < HOT16; ++i) dst[i] = src[i];
+        if (ag_in) for (int i = HOT16; i < ALL16; ++i) dst[i] = src[i];
+        else e.ag.err = 0;
+      }
       double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
       if (nb) {
         begin_step(e, ptr.mt_pol + (size_t)b * 312, D);
@@ -445,14 +457,39 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
           if (ready == -2) ready = -1;
         }
       }
+      if (ready >= 0 && !ag_in) {
+        // a step (or the warm-up) ended on an env whose agent block was not loaded: env_tick wrote the to-state, the
+        // reward and the ready kind into the local copy -- put them on top of the block in HBM
+        const int kind = e.ag.kind;
+        const double rew = e.ag.last_reward;
+        float tv[RLM_N_STATE_MAX];
+        for (int i = 0; i < RLM_N_STATE_MAX; ++i) tv[i] = (i < P.n_state_vars) ? e.ag.to_vars[i] : 0.0f;
+        const int4* src = (const int4*)g;
+        int4* dst = (int4*)&e;
+        for (int i = HOT16; i < ALL16; ++i) dst[i] = src[i];
+        e.ag.kind = kind;
+        if (kind == 0) {
+          e.ag.last_reward = rew; e.ag.hs_valid = 0;
+          for (int i = 0; i < RLM_N_STATE_MAX; ++i) if (i < P.n_state_vars) e.ag.to_vars[i] = tv[i];
+        }
+        ag_in = true;
+      }
       errs = (unsigned)(e.err | e.ag.err);
-      *g = e;
+      {
+        int4* dst = (int4*)g;
+        const int4* src = (const int4*)&e;
+        for (int i = 0; i < HOT16; ++i) dst[i] = src[i];
+        if (ag_in) for (int i = HOT16; i < ALL16; ++i) dst[i] = src[i];
+      }
     }
   }
-  {
-    const bool still = b < (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs) && ready < 0 && !only_begin &&
-                       ((EnvHdr*)(ptr.env + (size_t)b * P.env_stride))->phase != PH_DONE && !env_on_hold(*(EnvHdr*)(ptr.env + (size_t)b * P.env_stride));
-    const unsigned rm = __ballot_sync(FULL, D.hold && still);
+  if (D.hold) {  // split surface: envs still inside their step after this launch
+    bool still = false;
+    if (b < (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs) && ready < 0 && !only_begin) {
+      const EnvHdr* g = (const EnvHdr*)(ptr.env + (size_t)b * P.env_stride);
+      still = g->phase != PH_DONE && !env_on_hold(*g);
+    }
+    const unsigned rm = __ballot_sync(FULL, still);
     if (rm && lane == 0) atomicAdd(&ptr.counters[5], (unsigned long long)__popc(rm));
   }
   // ready list: one atomic per warp
@@ -604,11 +641,12 @@ __device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const D
       // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
       if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
       if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
-      if (!D.backtest && !P.shared_policy && P.algorithm < RLM_ALGO_R_LEARN) {
-        // The learner kernel's first act is 864 gathers from this env's weight table; they are DRAM misses, and an SM
-        // can only keep a few hundred of them in flight.  Hash the to-state here -- 31 lanes of this warp idle anyway --
-        // hand the sums over, and ask L2 for the 864 sectors now (prefetches carry no data back, so they do not queue
-        // behind the SM's miss tracking): they arrive under the tail of this kernel and the launch gap.
+      if (D.env_hash && !D.backtest && !P.shared_policy && P.algorithm < RLM_ALGO_R_LEARN) {
+        // OPTIONAL (RLM_ENV_HASH=1; off by default): hash the to-state here -- 31 lanes of this warp idle anyway -- hand
+        // the sums to the learner kernel and ask L2 for the step's 864 sectors now.  Measured on B200 at C1 (ncu,
+        // profiles/r2_c1_ncu_full_summary.txt): the prefetches DOUBLE the DRAM traffic (77 MB in this kernel, and the
+        // learner kernel still misses: one tick's 1.04 M sectors occupy 1.04 M 128-byte L2 lines = 133 MB > L2), and
+        // the extra 700 instructions cost this latency-bound kernel 6 us for 2 us saved in the learner.
         __syncwarp();
         const LnSums h = ln_hash(rlm_rndseq_table, e.ag.to_vars, false, lane);
         unsigned long long* hs = ptr.hsum + (size_t)env * 96;

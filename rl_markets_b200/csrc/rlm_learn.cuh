@@ -33,9 +33,10 @@ __host__ __device__ inline size_t ln_v_bytes(int is_double) { return (size_t)(is
 // adds the update to the weights it already holds instead of reading them back from L2 behind the reductions
 #define UT_SLOTS 1024
 #define UT_MAX_ENTRIES 512
-// learner scratch of one step: [V][tile table 4096][update table 8192][q_pre 2*9 doubles][dec 6 doubles]
+// learner scratch of one step: [V][tile table 4096][update table 8192][tile indices 27 x 32 ints][q_pre 2*9 doubles][dec 6 doubles]
+#define LN_IDX_BYTES (3 * RLM_MAX_ACTIONS * 32 * 4)
 __host__ __device__ inline size_t ln_scratch_bytes(int is_double) {
-  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
+  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + LN_IDX_BYTES + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
 }
 // per-warp shared memory of rlm_learn_kernel: [AgentD 704][scratch]
 __host__ __device__ inline size_t ln_warp_bytes(int is_double) { return (size_t)LN_AG_BYTES + ln_scratch_bytes(is_double); }
@@ -43,14 +44,22 @@ static_assert(sizeof(AgentD) <= LN_AG_BYTES, "agent block outgrew its shared-mem
 
 // ---- gathers K0 .. K0+N-1 (k = g*9 + a) of one table in flight together; raw weights -> V[a][g*32 + lane]
 template <int K0, int N>
-__device__ __forceinline__ void ln_gather_issue(const double* __restrict__ th, const LnSums& h, double* v) {
+__device__ __forceinline__ void ln_gather_issue(const double* __restrict__ th, const LnSums& h, double* v, int* idx = nullptr, int lane = 0) {
   const int A = P.n_actions;
   if (P.m_pow2) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + ln_tile<true>(h, K0 + k)) : 0.0;
+    for (int k = 0; k < N; ++k) {
+      const int f = ln_tile<true>(h, K0 + k);
+      v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + f) : 0.0;
+      if (idx) idx[(K0 + k) * 32 + lane] = f;
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < N; ++k) v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + ln_tile<false>(h, K0 + k)) : 0.0;
+    for (int k = 0; k < N; ++k) {
+      const int f = ln_tile<false>(h, K0 + k);
+      v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + f) : 0.0;
+      if (idx) idx[(K0 + k) * 32 + lane] = f;
+    }
   }
 }
 template <int K0, int N>
@@ -61,16 +70,17 @@ __device__ __forceinline__ void ln_gather_store(const double* v, int lane, doubl
     if (((K0 + k) % RLM_MAX_ACTIONS) < A) V[((K0 + k) % RLM_MAX_ACTIONS) * LN_VROW + ((K0 + k) / RLM_MAX_ACTIONS) * 32 + lane] = v[k];
 }
 template <bool DBL, int GB>
-__device__ __forceinline__ void ln_gather(const double* __restrict__ th_a, const double* __restrict__ th_b, const LnSums& h, int lane, double* V) {
+__device__ __forceinline__ void ln_gather(const double* __restrict__ th_a, const double* __restrict__ th_b, const LnSums& h, int lane, double* V,
+                                          int* idx = nullptr) {
   static_assert(GB == 27 || GB == 9, "gather batch: everything, or one feature group at a time");
   double v[GB];
   if (GB == 27) {
-    ln_gather_issue<0, GB>(th_a, h, v); ln_gather_store<0, GB>(v, lane, V);
+    ln_gather_issue<0, GB>(th_a, h, v, idx, lane); ln_gather_store<0, GB>(v, lane, V);
     if (DBL) { ln_gather_issue<0, GB>(th_b, h, v); ln_gather_store<0, GB>(v, lane, V + RLM_MAX_ACTIONS * LN_VROW); }
   } else {
-    ln_gather_issue<0, 9>(th_a, h, v); ln_gather_store<0, 9>(v, lane, V);
-    ln_gather_issue<9, 9>(th_a, h, v); ln_gather_store<9, 9>(v, lane, V);
-    ln_gather_issue<18, 9>(th_a, h, v); ln_gather_store<18, 9>(v, lane, V);
+    ln_gather_issue<0, 9>(th_a, h, v, idx, lane); ln_gather_store<0, 9>(v, lane, V);
+    ln_gather_issue<9, 9>(th_a, h, v, idx, lane); ln_gather_store<9, 9>(v, lane, V);
+    ln_gather_issue<18, 9>(th_a, h, v, idx, lane); ln_gather_store<18, 9>(v, lane, V);
     if (DBL) {
       double* Vb = V + RLM_MAX_ACTIONS * LN_VROW;
       ln_gather_issue<0, 9>(th_b, h, v); ln_gather_store<0, 9>(v, lane, Vb);
@@ -93,27 +103,23 @@ __device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every 
   while (atomicCAS(&ut[slot], HS_EMPTY, f) != HS_EMPTY) slot = (slot + 1) & (UT_SLOTS - 1);
   ((float*)(ut + UT_SLOTS))[slot] = ev;
 }
-template <bool POW2>
-__device__ __forceinline__ void ln_patch_local_t(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
+// idx: this step's 27 x 32 tile indices (row k = g*9 + a, column = lane), stored by the gather
+__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const int* idx, int lane, double* V) {
   const int A = P.n_actions;
   const float* uv = (const float*)(ut + UT_SLOTS);
-#pragma unroll
-  for (int k = 0; k < 3 * RLM_MAX_ACTIONS; ++k) {  // (unrolled: the sums stay in registers)
-    if ((k % RLM_MAX_ACTIONS) < A) {
-      const int f = ln_tile<POW2>(h, k);
-      unsigned slot = ut_hash(f);
-      int key = ut[slot];
-      while (key != HS_EMPTY && key != f) { slot = (slot + 1) & (UT_SLOTS - 1); key = ut[slot]; }
-      if (key == f) {
-        const int at = (k % RLM_MAX_ACTIONS) * LN_VROW + (k / RLM_MAX_ACTIONS) * 32 + lane;
-        V[at] = V[at] + scaled_update * (double)uv[slot];
-      }
+#pragma unroll 1
+  for (int k = 0; k < 3 * RLM_MAX_ACTIONS; ++k) {  // rolled on purpose: this runs once per step, code size is time
+    const int a = k % RLM_MAX_ACTIONS;
+    if (a >= A) continue;
+    const int f = idx[k * 32 + lane];
+    unsigned slot = ut_hash(f);
+    int key = ut[slot];
+    while (key != HS_EMPTY && key != f) { slot = (slot + 1) & (UT_SLOTS - 1); key = ut[slot]; }
+    if (key == f) {
+      const int at = a * LN_VROW + (k / RLM_MAX_ACTIONS) * 32 + lane;
+      V[at] = V[at] + scaled_update * (double)uv[slot];
     }
   }
-}
-__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
-  if (P.m_pow2) ln_patch_local_t<true>(ut, scaled_update, h, lane, V);
-  else ln_patch_local_t<false>(ut, scaled_update, h, lane, V);
 }
 
 // ---- exact-order sum of agent.cpp:117-135 over one action row of raw weights: 16 blocks of 8; block b+1 is loaded
@@ -314,7 +320,8 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
   double* V = (double*)scr;
   int* tt = (int*)(scr + ln_v_bytes(DBL ? 1 : 0));
   int* ut = tt + 2 * TT_SLOTS;
-  double* q_pre_a = (double*)(ut + 2 * UT_SLOTS);
+  int* idx_s = ut + 2 * UT_SLOTS;
+  double* q_pre_a = (double*)(idx_s + 3 * RLM_MAX_ACTIONS * 32);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   double* dec = q_pre_b + RLM_MAX_ACTIONS;
   const unsigned* rnd = rlm_rndseq_table;
@@ -388,10 +395,10 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
     LPH(2);
     if (DBL || GB != 27) {
       if (is_main) ln_tt_build(tt, ag, lane);
-      ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V);
+      ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V, idx_s);
     } else {
       double v[3 * RLM_MAX_ACTIONS];
-      ln_gather_issue<0, 27>(theta_a, h, v);
+      ln_gather_issue<0, 27>(theta_a, h, v, idx_s, lane);
       LPH(3);
       if (is_main) ln_tt_build(tt, ag, lane);  // under the gathers' round trip
       LPH(4);
@@ -458,7 +465,7 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
       steps_done++;
       LPH(13);
       if (!dbg_nopatch) {
-        if (local_patch) ln_patch_local(ut, scaled, h, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
+        if (local_patch) ln_patch_local(ut, scaled, idx_s, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
         else ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V);  // (long trace lists: read everything again)
       }
       LPH(14);

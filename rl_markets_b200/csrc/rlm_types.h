@@ -145,6 +145,8 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int n_sub;          // ... and its size (0 = the whole batch).  Sub-batches run on their own streams (rlm_api.cu)
   int sub_idx;        // index of the sub-batch (timeline probe of the RLM_TIMING build)
   int debug_flags;    // RLM_TIMING build only (RLM_DEBUG_FLAGS): what-if switches of tools/timeline_probe.py; results are wrong with any set
+  int env_hash;       // tick kernel hashes the to-state and prefetches its tiles at a step end (RLM_ENV_HASH=1; measured slower)
+  int pad2;
   int hold;           // split surface (rlm_env_step): envs whose step has ended, or whose next action is not applied yet, do not tick
 };
 
