@@ -78,6 +78,13 @@ struct rlm_handle_s {
   bool staged = false;  // learner: whole-table staging (memory_size * 8 <= 64 KB, independent single-table policies)
   cudaStream_t sub_stream[RLM_MAX_SUB] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[RLM_MAX_SUB] = {};
+  // round-paced engine (independent policies, warp-per-env ticks): see run_rounds
+  bool rounds = false;
+  int run_seq = 0;
+  int round_streams = 1;  // sub-batches of the round-paced engine, each on its own stream (RLM_ROUND_STREAMS)
+  int* h_live = nullptr;  // pinned [RLM_MAX_SUB][2]: ready count of the last round of each group in flight
+  cudaEvent_t ev_live[RLM_MAX_SUB][2] = {};
+  long long rounds_launched = 0, rounds_calls = 0;
 };
 
 // The kernels read their per-handle constants from ONE __constant__ block (rlm_env.cuh: P).  g_params_owner says whose
@@ -374,6 +381,12 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
   CK(cudaMalloc(&h->ptr.hsum, (size_t)cfg->n_envs * 3 * 32 * 8));
   h->ready_cap = 256;
   CK(cudaMalloc(&h->ptr.ready_count, (size_t)RLM_MAX_SUB * h->ready_cap * 4));
+  CK(cudaMalloc(&h->ptr.runctl, sizeof(RunCtl)));
+  CK(cudaMemset(h->ptr.runctl, 0, sizeof(RunCtl)));
+  CK(cudaMallocHost(&h->h_live, RLM_MAX_SUB * 2 * sizeof(int)));
+  for (int s = 0; s < RLM_MAX_SUB; ++s)
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_live[s][i], cudaEventDisableTiming));
+  if (const char* s = getenv("RLM_ROUND_STREAMS")) { const int v = atoi(s); if (v >= 1 && v <= RLM_MAX_SUB) h->round_streams = v; }
   // sub-batches of the tick-synchronous engine (see rlm_handle_s::n_sub); RLM_SUBBATCHES overrides
   h->n_sub = 1;  // (measured on B200: co-resident tick and learner kernels slow each other down as much as they overlap)
   h->staged = !h->hp.is_double && !cfg->shared_policy && cfg->memory_size * 8 <= 65536 && (cfg->memory_size % 2) == 0;
@@ -386,9 +399,9 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
   if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
   if (const char* s = getenv("RLM_GRAPHS")) h->use_graphs = atoi(s) != 0;
   if (const char* s = getenv("RLM_SUBBATCHES")) { const int v = atoi(s); if (v >= 1 && v <= RLM_MAX_SUB) h->n_sub = cfg->shared_policy ? 1 : v; }
-  if (h->n_sub > 1) {
+  if (std::max(h->n_sub, h->round_streams) > 1) {
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    for (int s = 0; s < h->n_sub; ++s) {
+    for (int s = 0; s < std::max(h->n_sub, h->round_streams); ++s) {
       CK(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->ev_join[s], cudaEventDisableTiming));
     }
@@ -422,6 +435,11 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
     // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
     h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
     if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
+    // the round-paced engine (RLM_ROUNDS=1) needs envs that never interact and the warp-per-env tick kernel.  Off by
+    // default: measured on B200 at C1 it is parity-green but slower than the tick-synchronous pair (8.9e6 env steps/s
+    // on one stream, 1.03e7 on eight, against 1.17e7) -- profiles/r2_round_engine.txt
+    h->rounds = false;
+    if (const char* s = getenv("RLM_ROUNDS")) h->rounds = atoi(s) != 0 && !cfg->shared_policy && h->env_variant == 0;
     if (const char* s = getenv("RLM_PDL")) rlm_set_pdl(atoi(s));  // programmatic dependent launch of the per-tick kernels (default off: slower when measured)
     if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
   }
@@ -448,6 +466,8 @@ int rlm_destroy(rlm_handle h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   cudaFree(h->ptr.ready); cudaFree(h->ptr.ready_count); cudaFree(h->ptr.occ); cudaFree(h->ptr.hsum);
+  cudaFree(h->ptr.runctl); if (h->h_live) cudaFreeHost(h->h_live);
+  for (auto& es : h->ev_live) for (auto e : es) if (e) cudaEventDestroy(e);
   cudaFree(h->ptr.q_slots); cudaFree(h->ptr.ag_done); cudaFree(h->d_qctl);
   for (auto e : h->ev) cudaEventDestroy(e);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
@@ -547,6 +567,7 @@ int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks) {
 }
 
 static int run_ticks_impl(rlm_handle h, int32_t n_ticks);
+static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks);
 
 int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
   API_LOCK;
@@ -560,6 +581,107 @@ int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
     h->consumed_valid[h->stream_buf] = true;
   }
   return rc;
+}
+
+// Round-paced engine.  A round = rlm_env_round_kernel (every live env ticks until its step ends or its n_ticks are used
+// up) + the learner kernel over the envs that came back ready.  How many rounds a call needs is only known on the
+// device (the env with the most steps in these n_ticks decides), so rounds are enqueued in groups of G -- one CUDA
+// graph each -- and after every group the ready count of its last round comes back through pinned memory: zero means
+// that every env has finished.  The host stays one group ahead of the device and stops when the group before the one it
+// has just enqueued reports zero; the rounds enqueued beyond the end find nothing to do (their CTAs return after one
+// load).  Unlike the tick-synchronous path the call therefore returns only when the device is (nearly) done.
+static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
+  const int B = h->cfg.n_envs;
+  RunCtl rc = {++h->run_seq, n_ticks, d.stream_off, d.stream_ticks, h->ptr.stream, 0};
+  CK(rlm_launch_runctl(h->ptr, rc, h->stream));
+  // sub-batches on their own streams: the learner kernel of one (throughput-bound: more steps than resident warps)
+  // runs while the tick kernel of another (latency-bound: a few serial ticks per env) does
+  const int S = std::max(1, std::min(h->round_streams, (B + 255) / 256));
+  int sub0[RLM_MAX_SUB + 1];
+  {
+    const int per = (((B + S - 1) / S) + 31) & ~31;
+    for (int s = 0; s <= S; ++s) sub0[s] = std::min(B, s * per);
+  }
+  int G = n_ticks >= 512 ? 32 : (n_ticks >= 128 ? 16 : 8);
+  G = std::min(std::min(G, n_ticks + 1), h->ready_cap);
+  const bool graphs = h->use_graphs && h->graph_warm;
+  h->graph_warm = true;  // (the first call launches directly: function attributes are set outside any capture)
+  DynParams dts[RLM_MAX_SUB];
+  DevPtrs pss[RLM_MAX_SUB];
+  cudaGraphExec_t exec[RLM_MAX_SUB] = {};
+  if (S > 1) CK(cudaEventRecord(h->ev_fork, h->stream));
+  for (int s = 0; s < S; ++s) {
+    cudaStream_t st = S > 1 ? h->sub_stream[s] : h->stream;
+    if (S > 1) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+    DynParams& dt = dts[s];
+    dt = d;
+    dt.n_ticks = 0; dt.stream_off = 0; dt.stream_ticks = 0; dt.env0 = sub0[s]; dt.n_sub = sub0[s + 1] - sub0[s]; dt.sub_idx = s;
+    DevPtrs& ps = pss[s];
+    ps = h->ptr;
+    ps.stream = nullptr;  // (read from *runctl: rlm_load_ticks swaps buffers between calls, the graphs stay)
+    ps.ready = h->ptr.ready + sub0[s];
+    ps.ready_count = h->ptr.ready_count + (size_t)s * h->ready_cap;
+    if (!graphs || dt.n_sub <= 0) continue;
+    for (auto& g : h->graphs)
+      if (g.chunk == -G && memcmp(&g.d, &dt, sizeof(DynParams)) == 0) exec[s] = g.exec;
+    if (!exec[s]) {
+      if (h->graphs.size() >= 24) {
+        CK(cudaStreamSynchronize(h->stream));
+        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+        h->graphs.clear();
+        for (int q = 0; q < s; ++q) exec[q] = nullptr;  // (re-captured below when launched directly this call)
+      }
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      cudaError_t ce = cudaMemsetAsync(ps.ready_count, 0, (size_t)G * 4, st);
+      for (int r = 0; r < G && ce == cudaSuccess; ++r) {
+        ce = rlm_launch_env_round(ps, dt, dt.n_sub, r, st);
+        if (ce == cudaSuccess) ce = launch_agent_on(h, ps, dt, r, 0, st);
+      }
+      cudaError_t ce2 = cudaStreamEndCapture(st, &graph);
+      if (ce != cudaSuccess || ce2 != cudaSuccess) { if (graph) cudaGraphDestroy(graph); CK(ce != cudaSuccess ? ce : ce2); }
+      ce = cudaGraphInstantiate(&exec[s], graph, 0);
+      cudaGraphDestroy(graph);
+      CK(ce);
+      h->graphs.push_back({-G, dt, exec[s]});
+    }
+  }
+  const int max_groups = (n_ticks + 1 + G - 1) / G + 1;  // a round advances every live env by at least one tick
+  bool live[RLM_MAX_SUB];
+  int n_live = 0;
+  for (int s = 0; s < S; ++s) { live[s] = sub0[s + 1] > sub0[s]; n_live += live[s] ? 1 : 0; }
+  h->rounds_calls++;
+  for (int k = 0; k <= max_groups && n_live > 0; ++k) {
+    for (int s = 0; s < S && k < max_groups; ++s) {
+      if (!live[s]) continue;
+      cudaStream_t st = S > 1 ? h->sub_stream[s] : h->stream;
+      if (exec[s]) CK(cudaGraphLaunch(exec[s], st));
+      else {
+        CK(cudaMemsetAsync(pss[s].ready_count, 0, (size_t)G * 4, st));
+        for (int r = 0; r < G; ++r) {
+          CK(rlm_launch_env_round(pss[s], dts[s], dts[s].n_sub, r, st));
+          CK(launch_agent_on(h, pss[s], dts[s], r, 0, st));
+        }
+      }
+      h->launches += 2 * G;
+      h->rounds_launched += G;
+      CK(cudaMemcpyAsync(h->h_live + 2 * s + (k & 1), pss[s].ready_count + (G - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(h->ev_live[s][k & 1], st));
+    }
+    if (k >= 1)
+      for (int s = 0; s < S; ++s) {
+        if (!live[s]) continue;
+        CK(cudaEventSynchronize(h->ev_live[s][(k - 1) & 1]));
+        if (h->h_live[2 * s + ((k - 1) & 1)] == 0) { live[s] = false; --n_live; }
+      }
+  }
+  if (n_live > 0) return fail(RLM_ERR_CUDA, "round-paced engine: envs still live after the last possible round");
+  if (S > 1)
+    for (int s = 0; s < S; ++s) {
+      CK(cudaEventRecord(h->ev_join[s], h->sub_stream[s]));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join[s], 0));
+    }
+  return RLM_OK;
 }
 
 static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
@@ -606,6 +728,7 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
     h->launches += 1;
     return RLM_OK;
   }
+  if (h->rounds && h->engine == 1 && !d.backtest && !d.hold && !h->profile && h->n_sub <= 1) return run_rounds(h, d, n_ticks);
   // two kernels per tick (env tick, then the learner step of the envs whose midprice moved), then one
   // trailing env pass that only runs the pending action selections, so that the observable state
   // after the call is "every env sits inside performAction's loop".  With n_sub > 1 every sub-batch does this on its own

@@ -556,8 +556,8 @@ __device__ __forceinline__ void envw_stage_out(EnvHdr* g, const EnvHdr* src_e, i
 
 // One market tick of the env staged in `w`, by its warp.  stream_pos: index of this tick in the resident stream chunk.
 // Returns -1, or the ready kind (0: a learner step ended -- state variables and reward are in e.ag; 1: warm-up ended).
-__device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const DevPtrs& ptr, const DynParams& D, int env, int stream_pos, int lane,
-                                         unsigned& ticked) {
+__device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const DevPtrs& ptr, const DynParams& D, int env, int stream_pos,
+                                         int stream_ticks, int lane, unsigned& ticked) {
   EnvHdr& e = *w.e;
   rlm_tick_msg& msg = *w.msg;
   double* pushv = w.pushv;
@@ -567,7 +567,7 @@ __device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const D
   if (P.source == RLM_SOURCE_GENERATOR) {
     flow_next_warp(&e.flow, &msg, w.r12, lane);
   } else {
-    if (stream_pos >= D.stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; have = false; }
+    if (stream_pos >= stream_ticks) { if (lane == 0) e.err |= ERR_STREAM_UNDERRUN; have = false; }
     else ((unsigned*)&msg)[lane] = __ldg((const unsigned*)(ptr.stream + ((size_t)stream_pos * P.n_envs + env)) + lane);
   }
   if (lane < RLM_NWIN) oldv[lane] = window_peek(e, ring, lane);  // issued early, consumed after the book logic
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
     if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
     __syncwarp();
   }
-  if (!only_begin && e.phase != PH_DONE) ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, lane, ticked);
+  if (!only_begin && e.phase != PH_DONE) ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, D.stream_ticks, lane, ticked);
   __syncwarp();
   envw_stage_out(g, &e, lane);
   if (!only_begin) KLOG_END(0);
@@ -711,6 +711,60 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
     if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
   }
 }
+
+// Round-paced tick kernel (independent policies): every env runs its OWN ticks until a step ends (or the run call's
+// ticks are used up), then waits for the learner kernel -- so a round is one learner step of EVERY live env instead of
+// the ~30 % whose midprice happened to move this tick, and the two launches' latencies are paid once per env step
+// instead of once per market tick.  Envs never exchange anything (own book, own stream, own weights), so the order in
+// which their ticks run is not observable: per env the sequence begin_step / tick / ... / learner step is the same as
+// in the tick-synchronous engine, bit for bit.  The per-call values live in *ptr.runctl (graphs are reused across calls).
+__global__ void __launch_bounds__(ENVW_WARPS * 32, 4) rlm_env_round_kernel(DevPtrs ptr, DynParams D, int tslot) {
+  PDL_PROLOGUE();
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env = D.env0 + blockIdx.x * ENVW_WARPS + warp;
+  KLOG_BEGIN(0);
+  if (env >= (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) return;
+  // an env is live exactly as long as it keeps coming back from the learner: no ready env a round ago, nothing to do
+  if (tslot > 0 && __ldcg(ptr.ready_count + tslot - 1) == 0) return;
+  const int4 rc4 = __ldg((const int4*)ptr.runctl);
+  const RunCtl rc = {rc4.x, rc4.y, rc4.z, rc4.w, nullptr, 0};
+  DevPtrs pt = ptr;
+  pt.stream = (const rlm_tick_msg*)__ldg((const unsigned long long*)ptr.runctl + 2);
+  const EnvWarp w = envw_carve(smem + (size_t)warp * envw_warp_bytes());
+  EnvHdr& e = *w.e;
+  EnvHdr* g = (EnvHdr*)(ptr.env + (size_t)env * P.env_stride);
+  double* ring = (double*)((unsigned char*)g + sizeof(EnvHdr));
+  envw_stage_in(&e, g, lane);
+  __syncwarp();
+  if (e.phase == PH_DONE) return;
+  int pos = e.run_id == rc.run_id ? e.run_pos : 0;
+  if (pos >= rc.n_ticks && !e.ag.need_begin) return;
+  int ready = -1;
+  unsigned ticked = 0;
+#pragma unroll 1
+  for (;;) {
+    if (e.ag.need_begin) {
+      if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
+      __syncwarp();
+    }
+    if (e.phase == PH_DONE || pos >= rc.n_ticks) break;
+    ready = envw_tick(w, ring, pt, D, env, rc.stream_off + pos, rc.stream_ticks, lane, ticked);
+    ++pos;
+    if (ready >= 0) break;
+  }
+  if (lane == 0) { e.run_id = rc.run_id; e.run_pos = pos; }
+  __syncwarp();
+  envw_stage_out(g, &e, lane);
+  KLOG_END(0);
+  if (lane == 0) {
+    if (ready >= 0) ptr.ready[atomicAdd(&ptr.ready_count[tslot], 1)] = env;
+    if (ticked) atomicAdd(&ptr.counters[0], (unsigned long long)ticked);
+    const unsigned errs = (unsigned)(e.err | e.ag.err);
+    if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
+  }
+}
+__global__ void rlm_runctl_kernel(RunCtl* dst, RunCtl v) { *dst = v; }
 
 // parity / profit-log record of one finished step (warp 0 of the CTA, or the env's warp).  Inlined into the training
 // kernel on purpose: as a call it costs the hot path ~200 bytes of register spills (ptxas call ABI).
@@ -1752,6 +1806,24 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
     attr = true;
   }
   return launch_pdl(rlm_env_kernel_w, (n_envs + ENVW_WARPS - 1) / ENVW_WARPS, ENVW_WARPS * 32, smem, st, ptr, D, tslot, only_begin);
+}
+
+cudaError_t rlm_launch_env_round(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, cudaStream_t st) {
+  const size_t smem = (size_t)ENVW_WARPS * envw_warp_bytes();
+  static bool attr = false;
+  if (!attr) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(rlm_env_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    cudaFuncSetAttribute(rlm_env_round_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
+    attr = true;
+  }
+  return launch_pdl(rlm_env_round_kernel, (n_envs + ENVW_WARPS - 1) / ENVW_WARPS, ENVW_WARPS * 32, smem, st, ptr, D, tslot);
+}
+cudaError_t rlm_launch_runctl(const DevPtrs& ptr, const RunCtl& v, cudaStream_t st) {
+  rlm_runctl_kernel<<<1, 1, 0, st>>>(ptr.runctl, v);
+  return cudaGetLastError();
 }
 
 cudaError_t rlm_launch_agent(const DevPtrs& ptr, const DynParams& D, int n_envs, int scratch_bytes, int tslot, int n_sms, int stage, cudaStream_t st) {

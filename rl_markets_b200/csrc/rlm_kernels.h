@@ -7,6 +7,8 @@ size_t rlm_scratch_bytes(int is_double);
 size_t rlm_agent_smem_bytes(int warps_per_cta, int scratch_bytes);
 cudaError_t rlm_upload_params(const DevParams* p);
 cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, int only_begin, int variant, cudaStream_t st);
+cudaError_t rlm_launch_env_round(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, cudaStream_t st);
+cudaError_t rlm_launch_runctl(const DevPtrs& ptr, const RunCtl& v, cudaStream_t st);
 cudaError_t rlm_launch_agent(const DevPtrs& ptr, const DynParams& D, int n_envs, int scratch_bytes, int tslot, int n_sms, int stage, cudaStream_t st);
 cudaError_t rlm_launch_agent3(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int occ_smem_words, int tslot, int n_sms, int stage, int full,
                               cudaStream_t st);

@@ -528,7 +528,13 @@ cudaError_t rlm_launch_learn(const DevPtrs& ptr, const DynParams& D, int n_envs,
                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rlm_learn_kernel<false>, LN_WARPS * 32, smem);
     per_sm[is_double ? 1 : 0] = (e == cudaSuccess && n > 0) ? n : 1;
   }
-  const int cap = n_sms * per_sm[is_double ? 1 : 0];  // one resident wave; the grid-stride loop takes the rest
+  // one resident wave; the grid-stride loop takes the rest.  RLM_LEARN_CTAS_PER_SM leaves room for the tick kernel of
+  // another sub-batch on the same SMs (round-paced engine with several streams)
+  static int per_sm_cap = -1;
+  if (per_sm_cap < 0) { const char* e = getenv("RLM_LEARN_CTAS_PER_SM"); per_sm_cap = e ? atoi(e) : 0; }
+  int ps = per_sm[is_double ? 1 : 0];
+  if (per_sm_cap > 0 && per_sm_cap < ps) ps = per_sm_cap;
+  const int cap = n_sms * ps;
   if (grid > cap) grid = cap;
   if (is_double) rlm_learn_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
   else rlm_learn_kernel<false><<<grid, LN_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(FU2_WARPS * 32, 2) rlm_fused2_kernel(DevPtrs p
   for (int t = 0; t < D.n_ticks; ++t) {
     if (e.phase == PH_DONE) break;
     int ready;
-    FUT(0, ready = envw_tick(w, ring, ptr, D, env, D.stream_off + t, lane, ticked));
+    FUT(0, ready = envw_tick(w, ring, ptr, D, env, D.stream_off + t, D.stream_ticks, lane, ticked));
 #ifdef RLM_TIMING
     fu_t[1]++;
 #endif

@@ -93,6 +93,8 @@ struct EnvHdr {
   // multi-message ticks of ingested real data (RLM_TICK_PARTIAL / RLM_TICK_TX_MORE, rlm_flow.h): the tick's prints and the
   // fills of its ApplyTransactions, kept until the last depth row of the tick has been applied
   int tick_open, txn;
+  // round-paced engine (rlm_env_round_kernel): ticks of run call `run_id` this env has consumed
+  int run_id, run_pos;
   float tx_px[RLM_TX_CAP];
   int tx_vol[RLM_TX_CAP];
   FillD tick_au, tick_bu;
@@ -150,6 +152,9 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int hold;           // split surface (rlm_env_step): envs whose step has ended, or whose next action is not applied yet, do not tick
 };
 
+// per-call parameters of the round-paced engine, in device memory so that its CUDA graphs do not depend on them
+struct RunCtl { int run_id, n_ticks, stream_off, stream_ticks; const rlm_tick_msg* stream; long long pad; };
+
 struct DevPtrs {
   unsigned char* env;       // [n_envs][env_stride]
   double* theta;            // [n_policies][M]
@@ -176,4 +181,5 @@ struct DevPtrs {
   int* ag_done;                  // [n_envs] agent -> env completion flags
   int q_size;                    // power of two >= n_envs
   int pad;
+  RunCtl* runctl;                // round-paced engine: the current run call
 };

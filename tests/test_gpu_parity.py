@@ -131,6 +131,8 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
     ({"RLM_ENGINE": "F"}, "double_q_learn"),
     ({"RLM_ENGINE": "s"}, "q_learn"),             # tick-synchronous engine (two launches per tick)
     ({"RLM_ENGINE": "s", "RLM_AGENT_VARIANT": "3"}, "sarsa"),  # ... with the round-1 three-warp learner kernel
+    ({"RLM_ROUNDS": "1"}, "q_learn"),             # round-paced engine (rlm_env_round_kernel): every env ticks to its step end
+    ({"RLM_ROUNDS": "1"}, "double_q_learn"),
 ])
 def test_every_engine_variant_matches_oracle(rlm, oracle, monkeypatch, env_vars, algo):
     """The non-default kernels (selected by environment variables read in rlm_create) are held to the same bar."""
@@ -146,5 +148,40 @@ def test_every_engine_variant_matches_oracle(rlm, oracle, monkeypatch, env_vars,
         recs, _keep = m.records(b)
         assert len(recs) == port["steps"] > 100
         _compare_env(recs, port, "%s %r env %d" % (algo, env_vars, b))
+        assert bytes(m.theta(b, 0)) == bytes((C.c_double * M)(*port["theta"]))
+    m.close()
+
+
+@pytest.mark.parametrize("streams", [1, 3])
+def test_round_paced_engine_on_a_chunked_stream(rlm, oracle, monkeypatch, streams):
+    """RLM_ROUNDS=1 with sub-batches on their own streams, several run calls per loaded chunk and a chunk swap in between
+    (the engine's CUDA graphs outlive rlm_load_ticks; the stream pointer travels through device memory)."""
+    monkeypatch.setenv("RLM_ROUNDS", "1")
+    monkeypatch.setenv("RLM_ROUND_STREAMS", str(streams))
+    n_envs, n_ticks, M = 70, 900, 4096
+    y, cfg = _mk("q_learn", M, n_envs, flow_seed=29, rec_cap=500, source=abi.SOURCE_STREAM)
+    check = [0, 33, 69]
+    per_env = {b: oracle.generate_ticks(cfg, b, n_ticks) for b in check}
+    filler = rlm.flow_generate(cfg.flow, 1, 0, n_ticks)
+    msgs = (abi.TickMsg * (n_ticks * n_envs))()
+    for t in range(n_ticks):
+        for b in range(n_envs):
+            msgs[t * n_envs + b] = per_env[b][t] if b in per_env else filler[t]
+    m = rlm.BatchedMarket(cfg)
+    base, per_tick = C.addressof(msgs), n_envs * C.sizeof(abi.TickMsg)
+    m.load_ticks(base, 500)
+    m.run_ticks(150)
+    m.run_ticks(150)
+    m.run_ticks(200)
+    m.load_ticks(base + 500 * per_tick, 400)
+    m.run_ticks(1)
+    m.run_ticks(399)
+    m.sync()
+    assert m.counters().ticks == n_envs * (n_ticks - 1)
+    for b in check:
+        port = oracle.run_port(cfg, b, per_env[b])
+        recs, _keep = m.records(b)
+        assert len(recs) == port["steps"] > 100
+        _compare_env(recs, port, "round-paced, %d streams, env %d" % (streams, b))
         assert bytes(m.theta(b, 0)) == bytes((C.c_double * M)(*port["theta"]))
     m.close()
