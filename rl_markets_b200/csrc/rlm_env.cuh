@@ -450,7 +450,10 @@ __device__ __noinline__ void next_state_tail(EnvHdr& e, const Fill& au, const Fi
   e.position += bu.volume + au.volume + as.volume;  // RiskManager::Update (risk_manager.cpp:34-39)
   check_orders(e);
   double mid = m_midprice(e);
-  long long mpt = to_ticks(mid, &e.err);
+  // (memo: ToTicks is a pure function of the price; a zero-initialised memo can only match mid == 0, which is recomputed)
+  long long mpt;
+  if (mid == e.tk_px && mid > 0.0) mpt = e.tk_ticks;
+  else { const int t = to_ticks(mid, &e.err); mpt = t; e.tk_px = mid; e.tk_ticks = t; }
   double mpm = mid - m_last_midprice(e), sp = m_spread(e);
   pushv[W_MID] = (double)mpt;
   pushv[W_VLT] = (double)mpt;

@@ -107,17 +107,23 @@ __device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every 
 __device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const int* idx, int lane, double* V) {
   const int A = P.n_actions;
   const float* uv = (const float*)(ut + UT_SLOTS);
+  // rolled over the actions (this runs once per step: code size is time), the three feature groups of one action side by
+  // side: three independent index -> hash -> key chains per iteration instead of one
 #pragma unroll 1
-  for (int k = 0; k < 3 * RLM_MAX_ACTIONS; ++k) {  // rolled on purpose: this runs once per step, code size is time
-    const int a = k % RLM_MAX_ACTIONS;
-    if (a >= A) continue;
-    const int f = idx[k * 32 + lane];
-    unsigned slot = ut_hash(f);
-    int key = ut[slot];
-    while (key != HS_EMPTY && key != f) { slot = (slot + 1) & (UT_SLOTS - 1); key = ut[slot]; }
-    if (key == f) {
-      const int at = a * LN_VROW + (k / RLM_MAX_ACTIONS) * 32 + lane;
-      V[at] = V[at] + scaled_update * (double)uv[slot];
+  for (int a = 0; a < A; ++a) {
+    int f[3], key[3];
+    unsigned slot[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) f[g] = idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) { slot[g] = ut_hash(f[g]); key[g] = ut[slot[g]]; }
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      while (key[g] != HS_EMPTY && key[g] != f[g]) { slot[g] = (slot[g] + 1) & (UT_SLOTS - 1); key[g] = ut[slot[g]]; }
+      if (key[g] == f[g]) {
+        const int at = a * LN_VROW + g * 32 + lane;
+        V[at] = V[at] + scaled_update * (double)uv[slot[g]];
+      }
     }
   }
 }
@@ -495,6 +501,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 5) rlm_learn_kernel(DevPtrs ptr
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wsm = smem + (size_t)warp * ln_warp_bytes(DBL ? 1 : 0);
+  // the 8 KB hashing table is read at random through L1, which is cold at launch: pull its 64 lines in now, under the
+  // ready-count and agent-block round trips, instead of missing on them one dependent batch at a time while hashing
+  if (threadIdx.x < 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(rlm_rndseq_table + threadIdx.x * 32));
   const int n_ready = ptr.ready_count[tslot];
   unsigned long long steps_done = 0, sum_z = 0;
   if (n_ready > (int)blockIdx.x) KLOG_BEGIN(1);

@@ -95,6 +95,9 @@ struct EnvHdr {
   int tick_open, txn;
   // round-paced engine (rlm_env_round_kernel): ticks of run call `run_id` this env has consumed
   int run_id, run_pos;
+  // Market::ToTicks of the last midprice (next_state_tail): the midprice moves on fewer than a third of the ticks
+  double tk_px;
+  int tk_ticks, tk_pad;
   float tx_px[RLM_TX_CAP];
   int tx_vol[RLM_TX_CAP];
   FillD tick_au, tick_bu;
