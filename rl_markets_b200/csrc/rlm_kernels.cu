@@ -9,14 +9,18 @@
 //                lane-interleaved local memory, SIMT over 32 envs.  An env whose midprice moved
 //                (Base::performAction's do-while, base.cpp:285-305) finishes the step, writes its state
 //                variables and reward, and appends itself to the tick's ready list.
-//   learner step rlm_agent3_kernel: one CTA of three warps per ready env (warp g = feature group g, lane j =
-//                tiling j, N_TILINGS == 32 == warp width): tile hashing, theta gathers, exact-order Q sums, the
-//                fused trace-decay/clear/set/theta-update pass (Agent::HandleTransition, src/rl/agent.cpp:86-101)
-//                and Q(from,.) for the next action selection.  rlm_agent_kernel<8>: one warp per env (older).
+//   learner step rlm_learn_kernel (rlm_learn.cuh): ONE warp per ready env (lane j = tiling j of all three feature
+//                groups, N_TILINGS == 32 == warp width): tile hashing, theta gathers, exact-order Q sums, the fused
+//                trace-decay/clear/set/theta-update pass (Agent::HandleTransition, src/rl/agent.cpp:86-101) and
+//                Q(from,.) for the next action selection.  rlm_learn_staged_kernel: the same step with the env's whole
+//                weight table staged in shared memory by one TMA bulk copy (memory_size * 8 <= 64 KB).
+//                rlm_agent3_kernel (round 1: one CTA of three warps per env, warp g = feature group g) serves the
+//                R-learning agents, the backtest step and batches above 16 384 envs; rlm_agent_kernel<8> is older still.
 //
 // The next tick's env kernel starts each stepped env with Learner::_step's action selection and DoAction
-// (serial.cpp:55-61, base.cpp:254-284), which is scalar work again.  rlm_run_kernel (persistent) and
-// rlm_fused_kernel are alternative single-launch engines, parity-green but slower (RLM_ENGINE=p|f).
+// (serial.cpp:55-61, base.cpp:254-284), which is scalar work again.  Alternative engines, all parity-green and all
+// slower on a B200: rlm_env_round_kernel (round-paced: every env ticks to its next step end),
+// rlm_fused2_kernel (rlm_learn.cuh), rlm_run_kernel (persistent queue) and rlm_fused_kernel (RLM_ENGINE=F|p|f).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #define RLM_TABLE_QUAL static __device__ const

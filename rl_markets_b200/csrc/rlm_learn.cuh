@@ -16,7 +16,7 @@
 //     tile -> last-writer table per entry, RED.ADD.F64 at L2); the second evaluation does not read anything back: it
 //     adds this step's updates (kept in a shared-memory table) to the weights the first evaluation gathered;
 //   * no occupancy bitmap: tables are dense after the first thousands of steps, which is the regime that counts.
-// ~2000 warp-instructions per step instead of ~7700, no __syncthreads, no spills at 128 registers.
+// ~4000 warp-instructions per step instead of ~7700, no __syncthreads, no spills at 128 registers.
 #pragma once
 
 #define LN_WARPS 3
