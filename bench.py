@@ -230,6 +230,24 @@ def measure(ctx, name, args, steps, warmup, headline):
     total_ms = evs[0].elapsed_time(evs[-1])
     steps_done, ticks_done, z_sum = c1.steps - c0.steps, c1.ticks - c0.ticks, c1.sum_traces - c0.sum_traces
     launches = c1.kernel_launches - c0.kernel_launches
+    # ---- per-kernel pass (untimed, right after the timed region, same state): CUDA events on the launching stream around
+    # every tick kernel and every learner kernel (direct launches; rlm_set_profiling) -> the dominant kernel's average
+    # launch duration for the roofline block
+    kt = None
+    prof_ticks = 0 if (shared and ctx.world > 1) else min(ticks, 128)
+    if prof_ticks > 0 and os.environ.get("RLM_ENGINE", "s")[:1] == "s" and not os.environ.get("RLM_ROUNDS"):
+        try:
+            m.set_profiling(True)
+            cp0 = m.counters()
+            m.run_ticks(prof_ticks)
+            m.sync()
+            cp1 = m.counters()
+            kt = dict(m.kernel_times())
+            kt.update({"steps": cp1.steps - cp0.steps, "z": cp1.sum_traces - cp0.sum_traces, "ticks": prof_ticks})
+        except Exception:
+            kt = None
+        finally:
+            m.set_profiling(False)
     total_ms = _allreduce(ctx, [total_ms], "MAX")[0]
     steps_all, ticks_all, z_all = _allreduce(ctx, [steps_done, ticks_done, z_sum], "SUM")
     if cold is not None:
@@ -274,6 +292,34 @@ def measure(ctx, name, args, steps, warmup, headline):
                               + ("" if M > 8192 else " (tables of <= 64 KB are staged whole by cp.async.bulk instead: this ceiling does not apply)")},
             },
         }
+        if kt and kt["agent_launches"] > 0 and kt["env_launches"] > 0 and kt["steps"] > 0:
+            # dominant kernel = the one with the larger share of a tick.  Algorithmic bytes per launch:
+            # learner kernel: steps x (B_q + 28 Z); tick kernel: envs x (B_msg + B_ring) + steps x 2 S_env
+            spl = kt["steps"] / float(kt["agent_launches"])
+            zpl = kt["z"] / float(max(kt["steps"], 1))
+            learner = {"kernel": "learner kernel (one launch per market tick: the learner steps of the envs whose midprice moved)",
+                       "avg_launch_ms": kt["agent_ms"] / kt["agent_launches"], "env_steps_per_launch": spl,
+                       "algorithmic_bytes_per_launch": spl * ((27648.0 if is_dq else 13824.0) + 28.0 * zpl)}
+            tick = {"kernel": "market tick kernel (one launch per market tick, every env)",
+                    "avg_launch_ms": kt["env_ms"] / kt["env_launches"], "envs_per_launch": B,
+                    "algorithmic_bytes_per_launch": B * 208.0 + spl * 1280.0}
+            for k in (learner, tick):
+                k["achieved"] = k["algorithmic_bytes_per_launch"] / (k["avg_launch_ms"] * 1e-3) / 1e9
+                k["frac"] = k["achieved"] / peak
+            dom, oth = (learner, tick) if learner["avg_launch_ms"] >= tick["avg_launch_ms"] else (tick, learner)
+            share = dom["avg_launch_ms"] / (learner["avg_launch_ms"] + tick["avg_launch_ms"])
+            rf = res["roofline"]
+            rf["whole_path"] = {"achieved": rf["achieved"], "frac": rf["frac"], "frac_nominal_8TBs": rf["frac_nominal_8TBs"],
+                                "algorithmic_bytes_per_env_step": rf["algorithmic_bytes_per_env_step"],
+                                "note": "env steps/s of the timed region x B_step (SURVEY 8d), both kernels and the launch gaps"}
+            rf.update({"kernel": dom["kernel"], "achieved": dom["achieved"], "frac": dom["frac"], "frac_nominal_8TBs": dom["achieved"] / 8000.0,
+                       "avg_launch_ms": dom["avg_launch_ms"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                       "share_of_tick_kernel_time": share,
+                       "timing": "CUDA events on the launching stream around every launch of %d market ticks run right after the timed "
+                                 "region in the same state (direct launches; rlm_set_profiling); per GPU, rank 0" % kt["ticks"],
+                       "other_kernel": {k: oth[k] for k in ("kernel", "avg_launch_ms", "algorithmic_bytes_per_launch", "achieved", "frac")}})
+            if dom is learner:
+                rf["env_steps_per_launch"] = spl
         if cold is not None:
             res["cold_start"] = {"value": cold["steps"] / (cold["ms"] * 1e-3), "unit": "env_steps/s",
                                  "note": "first bench step of training from all-zero weight tables; informational"}
@@ -283,8 +329,16 @@ def measure(ctx, name, args, steps, warmup, headline):
             with open(os.path.join(ROOT, "profiles", "r2_summary.json")) as f:
                 prof = json.load(f).get(name)
             if prof:
-                res["roofline"]["traffic"] = prof["dram_bytes_per_env_step"] * res["roofline"]["env_steps_per_launch"]
-                res["roofline"]["traffic_source"] = prof.get("source")
+                rf = res["roofline"]
+                per_step = prof["dram_bytes_per_env_step"]
+                spl_now = rf["env_steps_per_launch"]
+                if "whole_path" in rf:  # the dominant kernel's own DRAM bytes per launch, scaled to this run's steps per launch
+                    lk = [v for k, v in prof.get("kernels", {}).items() if ("learn" in k or "agent" in k) == rf["kernel"].startswith("learner")]
+                    if lk:
+                        per_step = (lk[0]["dram_read_bytes"] + lk[0]["dram_write_bytes"]) / float(prof["env_steps_in_captured_tick"])
+                    spl_now = kt["steps"] / float(kt["agent_launches"])
+                rf["traffic"] = per_step * spl_now
+                rf["traffic_source"] = prof.get("source")
         except Exception:
             pass
     return res, m, cfg, (B, M, algo, ticks)

@@ -31,7 +31,6 @@ int rlm_set_error_(int code, const std::string& msg) { return fail(code, msg); }
                                        std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
-#define RLM_MAX_SUB 8
 struct rlm_handle_s {
   rlm_config cfg;
   DevParams hp;
@@ -376,11 +375,13 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
   if (const char* s = getenv("RLM_DEBUG_FLAGS")) h->dyn.debug_flags = atoi(s);
 #endif
   if (const char* s = getenv("RLM_ENV_HASH")) h->dyn.env_hash = atoi(s) != 0;
+  if (const char* s = getenv("RLM_ROUND_CAP")) h->dyn.round_cap = std::max(0, atoi(s));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaMalloc(&h->ptr.ready, (size_t)cfg->n_envs * 4));
   CK(cudaMalloc(&h->ptr.hsum, (size_t)cfg->n_envs * 3 * 32 * 8));
-  h->ready_cap = 256;
-  CK(cudaMalloc(&h->ptr.ready_count, (size_t)RLM_MAX_SUB * h->ready_cap * 4));
+  h->ready_cap = RLM_READY_CAP;
+  CK(cudaMalloc(&h->ptr.ready_count, (size_t)2 * RLM_LIVE_OFF * 4));  // ready counters + live counters (rlm_types.h)
+  CK(cudaMemset(h->ptr.ready_count, 0, (size_t)2 * RLM_LIVE_OFF * 4));
   CK(cudaMalloc(&h->ptr.runctl, sizeof(RunCtl)));
   CK(cudaMemset(h->ptr.runctl, 0, sizeof(RunCtl)));
   CK(cudaMallocHost(&h->h_live, RLM_MAX_SUB * 2 * sizeof(int)));
@@ -634,6 +635,7 @@ static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
       cudaGraph_t graph = nullptr;
       CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       cudaError_t ce = cudaMemsetAsync(ps.ready_count, 0, (size_t)G * 4, st);
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(ps.ready_count + RLM_LIVE_OFF, 0, (size_t)G * 4, st);
       for (int r = 0; r < G && ce == cudaSuccess; ++r) {
         ce = rlm_launch_env_round(ps, dt, dt.n_sub, r, st);
         if (ce == cudaSuccess) ce = launch_agent_on(h, ps, dt, r, 0, st);
@@ -658,6 +660,7 @@ static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
       if (exec[s]) CK(cudaGraphLaunch(exec[s], st));
       else {
         CK(cudaMemsetAsync(pss[s].ready_count, 0, (size_t)G * 4, st));
+        CK(cudaMemsetAsync(pss[s].ready_count + RLM_LIVE_OFF, 0, (size_t)G * 4, st));
         for (int r = 0; r < G; ++r) {
           CK(rlm_launch_env_round(pss[s], dts[s], dts[s].n_sub, r, st));
           CK(launch_agent_on(h, pss[s], dts[s], r, 0, st));
@@ -665,7 +668,7 @@ static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
       }
       h->launches += 2 * G;
       h->rounds_launched += G;
-      CK(cudaMemcpyAsync(h->h_live + 2 * s + (k & 1), pss[s].ready_count + (G - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h->h_live + 2 * s + (k & 1), pss[s].ready_count + RLM_LIVE_OFF + (G - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaEventRecord(h->ev_live[s][k & 1], st));
     }
     if (k >= 1)

@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
 // rolling window each (ring loads are issued first so their HBM/L2 round trips overlap the book logic),
 // lanes 0..7 each evaluate one state variable at a step end.  No env waits for another one: a warp whose
 // env needs the learner step just appends it to the ready list.
-#define ENVW_WARPS 8
+#define ENVW_WARPS 8  // most warps per CTA (launch bounds)
+#define ENVW_WARPS_DEFAULT 8
 // per-warp shared memory of the tick: [EnvHdr][message 128][pushv, oldv: 2 x 10 doubles][flag 16, Philox 48, fills + errs 64]
 __host__ __device__ inline size_t envw_hdr_bytes() { return (sizeof(EnvHdr) + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t envw_warp_bytes() { return envw_hdr_bytes() + 128 + 8 * 2 * RLM_NWIN + 128; }
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   PDL_PROLOGUE();
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int env = D.env0 + blockIdx.x * ENVW_WARPS + warp;
+  const int env = D.env0 + blockIdx.x * (blockDim.x >> 5) + warp;  // (warps per CTA: rlm_launch_env, <= ENVW_WARPS)
   if (!only_begin) KLOG_BEGIN(0);
   if (env >= (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) return;
   const EnvWarp w = envw_carve(smem + (size_t)warp * envw_warp_bytes());
@@ -726,11 +727,13 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32, 4) rlm_env_round_kernel(DevPt
   PDL_PROLOGUE();
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int env = D.env0 + blockIdx.x * ENVW_WARPS + warp;
+  const int env = D.env0 + blockIdx.x * (blockDim.x >> 5) + warp;
   KLOG_BEGIN(0);
   if (env >= (D.n_sub > 0 ? D.env0 + D.n_sub : P.n_envs)) return;
-  // an env is live exactly as long as it keeps coming back from the learner: no ready env a round ago, nothing to do
-  if (tslot > 0 && __ldcg(ptr.ready_count + tslot - 1) == 0) return;
+  // live envs of a round = those that left it with a learner step due or with ticks of this call still to run (counted
+  // behind the ready counters): none a round ago, nothing to do
+  int* live_count = ptr.ready_count + RLM_LIVE_OFF;
+  if (tslot > 0 && __ldcg(live_count + tslot - 1) == 0) return;
   const int4 rc4 = __ldg((const int4*)ptr.runctl);
   const RunCtl rc = {rc4.x, rc4.y, rc4.z, rc4.w, nullptr, 0};
   DevPtrs pt = ptr;
@@ -746,15 +749,19 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32, 4) rlm_env_round_kernel(DevPt
   if (pos >= rc.n_ticks && !e.ag.need_begin) return;
   int ready = -1;
   unsigned ticked = 0;
+  // D.round_cap > 0 bounds the ticks of one round: an env whose step has not ended by then simply comes back in the
+  // next round, so that a round's tick kernel does not wait for the env with the longest run of unchanged midprices
+  const int cap = D.round_cap > 0 ? D.round_cap : 0x7fffffff;
+  int n_run = 0;
 #pragma unroll 1
   for (;;) {
     if (e.ag.need_begin) {
       if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
       __syncwarp();
     }
-    if (e.phase == PH_DONE || pos >= rc.n_ticks) break;
+    if (e.phase == PH_DONE || pos >= rc.n_ticks || n_run >= cap) break;
     ready = envw_tick(w, ring, pt, D, env, rc.stream_off + pos, rc.stream_ticks, lane, ticked);
-    ++pos;
+    ++pos; ++n_run;
     if (ready >= 0) break;
   }
   if (lane == 0) { e.run_id = rc.run_id; e.run_pos = pos; }
@@ -763,6 +770,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32, 4) rlm_env_round_kernel(DevPt
   KLOG_END(0);
   if (lane == 0) {
     if (ready >= 0) ptr.ready[atomicAdd(&ptr.ready_count[tslot], 1)] = env;
+    if (ready >= 0 || (e.phase != PH_DONE && pos < rc.n_ticks)) atomicAdd(&live_count[tslot], 1);
     if (ticked) atomicAdd(&ptr.counters[0], (unsigned long long)ticked);
     const unsigned errs = (unsigned)(e.err | e.ag.err);
     if (errs) atomicOr(&ptr.counters[4], (unsigned long long)errs);
@@ -1788,6 +1796,16 @@ int rlm_run_max_resident_ctas(int scratch_bytes, int n_sms) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// warps (= envs) per CTA of the warp-per-env tick kernels: 4 096 envs are 512 CTAs of 8 warps, i.e. 3 or 4 CTAs per SM --
+// smaller CTAs spread them evenly (RLM_ENVW_WARPS = 1, 2, 4 or 8)
+static int envw_warps_per_cta() {
+  static int w = 0;
+  if (!w) {
+    w = ENVW_WARPS_DEFAULT;
+    if (const char* e = getenv("RLM_ENVW_WARPS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) w = v; }
+  }
+  return w;
+}
 cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, int only_begin, int variant, cudaStream_t st) {
   if (D.n_sub > 0) n_envs = D.n_sub;  // one sub-batch
   if (variant == 1) {  // one thread per env (SIMT over envs)
@@ -1797,7 +1815,8 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
     rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
     return cudaGetLastError();
   }
-  const size_t smem = ENVW_WARPS * envw_warp_bytes();
+  const int W = envw_warps_per_cta();
+  const size_t smem = (size_t)W * envw_warp_bytes();
   static bool attr = false;
   if (!attr) {
     if (smem > 48 * 1024) {
@@ -1809,11 +1828,12 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
     cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
     attr = true;
   }
-  return launch_pdl(rlm_env_kernel_w, (n_envs + ENVW_WARPS - 1) / ENVW_WARPS, ENVW_WARPS * 32, smem, st, ptr, D, tslot, only_begin);
+  return launch_pdl(rlm_env_kernel_w, (n_envs + W - 1) / W, W * 32, smem, st, ptr, D, tslot, only_begin);
 }
 
 cudaError_t rlm_launch_env_round(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, cudaStream_t st) {
-  const size_t smem = (size_t)ENVW_WARPS * envw_warp_bytes();
+  const int W = envw_warps_per_cta();
+  const size_t smem = (size_t)W * envw_warp_bytes();
   static bool attr = false;
   if (!attr) {
     if (smem > 48 * 1024) {
@@ -1823,7 +1843,7 @@ cudaError_t rlm_launch_env_round(const DevPtrs& ptr, const DynParams& D, int n_e
     cudaFuncSetAttribute(rlm_env_round_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
     attr = true;
   }
-  return launch_pdl(rlm_env_round_kernel, (n_envs + ENVW_WARPS - 1) / ENVW_WARPS, ENVW_WARPS * 32, smem, st, ptr, D, tslot);
+  return launch_pdl(rlm_env_round_kernel, (n_envs + W - 1) / W, W * 32, smem, st, ptr, D, tslot);
 }
 cudaError_t rlm_launch_runctl(const DevPtrs& ptr, const RunCtl& v, cudaStream_t st) {
   rlm_runctl_kernel<<<1, 1, 0, st>>>(ptr.runctl, v);

@@ -19,7 +19,10 @@
 // ~4000 warp-instructions per step instead of ~7700, no __syncthreads, no spills at 128 registers.
 #pragma once
 
-#define LN_WARPS 3
+#ifndef LN_WARPS
+#define LN_WARPS 3  // steps (warps) per CTA; resident CTAs per SM follow from the shared memory of a step
+#endif
+#define LN_MIN_CTAS (15 / LN_WARPS)  // register budget: 15 warps per SM (128 registers)
 #ifdef RLM_TIMING
 #define LPH(i) do { if (lane == 0 && tp_idx < 4096) g_phase_clk[tp_idx * 16 + (i)] = clock64(); } while (0)
 #else
@@ -31,8 +34,11 @@
 __host__ __device__ inline size_t ln_v_bytes(int is_double) { return (size_t)(is_double ? 2 : 1) * RLM_MAX_ACTIONS * LN_VROW * 8; }
 // feature -> eligibility of every weight this step's update moved (open addressing): the second evaluation of the step
 // adds the update to the weights it already holds instead of reading them back from L2 behind the reductions
-#define UT_SLOTS 1024
-#define UT_MAX_ENTRIES 512
+#ifndef UT_LOG2
+#define UT_LOG2 10
+#endif
+#define UT_SLOTS (1 << UT_LOG2)
+#define UT_MAX_ENTRIES (UT_SLOTS / 2)
 // learner scratch of one step: [V][tile table 4096][update table 8192][tile indices 27 x 32 ints][q_pre 2*9 doubles][dec 6 doubles]
 #define LN_IDX_BYTES (3 * RLM_MAX_ACTIONS * 32 * 4)
 __host__ __device__ inline size_t ln_scratch_bytes(int is_double) {
@@ -92,7 +98,7 @@ __device__ __forceinline__ void ln_gather(const double* __restrict__ th_a, const
 
 // second evaluation of a step (same state, theta after this env's own update): theta_new[f] = theta_old[f] + update[f],
 // the one IEEE addition the L2 reduction performs, on the weight the first evaluation gathered -- no read-back
-__device__ __forceinline__ unsigned ut_hash(int f) { return ((unsigned)f * 2654435761u) >> 22; }  // 10 bits
+__device__ __forceinline__ unsigned ut_hash(int f) { return ((unsigned)f * 2654435761u) >> (32 - UT_LOG2); }
 __device__ __forceinline__ void ut_clear(int* ut, int lane) {
   int4* k4 = (int4*)ut;
 #pragma unroll
@@ -497,13 +503,13 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
 }
 
 template <bool DBL>
-__global__ void __launch_bounds__(LN_WARPS * 32, 5) rlm_learn_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
+__global__ void __launch_bounds__(LN_WARPS * 32, LN_MIN_CTAS) rlm_learn_kernel(DevPtrs ptr, DynParams D, int tslot, int stage) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wsm = smem + (size_t)warp * ln_warp_bytes(DBL ? 1 : 0);
   // the 8 KB hashing table is read at random through L1, which is cold at launch: pull its 64 lines in now, under the
   // ready-count and agent-block round trips, instead of missing on them one dependent batch at a time while hashing
-  if (threadIdx.x < 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(rlm_rndseq_table + threadIdx.x * 32));
+  for (int i = threadIdx.x; i < 64; i += LN_WARPS * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(rlm_rndseq_table + i * 32));
   const int n_ready = ptr.ready_count[tslot];
   unsigned long long steps_done = 0, sum_z = 0;
   if (n_ready > (int)blockIdx.x) KLOG_BEGIN(1);

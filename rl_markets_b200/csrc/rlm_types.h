@@ -151,9 +151,14 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int sub_idx;        // index of the sub-batch (timeline probe of the RLM_TIMING build)
   int debug_flags;    // RLM_TIMING build only (RLM_DEBUG_FLAGS): what-if switches of tools/timeline_probe.py; results are wrong with any set
   int env_hash;       // tick kernel hashes the to-state and prefetches its tiles at a step end (RLM_ENV_HASH=1; measured slower)
-  int pad2;
+  int round_cap;      // round-paced engine: most ticks an env runs in one round (RLM_ROUND_CAP; 0 = up to its step end)
   int hold;           // split surface (rlm_env_step): envs whose step has ended, or whose next action is not applied yet, do not tick
 };
+
+// ready counters: [RLM_MAX_SUB][RLM_READY_CAP] ints, followed by as many live counters (round-paced engine)
+#define RLM_MAX_SUB 8
+#define RLM_READY_CAP 256
+#define RLM_LIVE_OFF (RLM_MAX_SUB * RLM_READY_CAP)
 
 // per-call parameters of the round-paced engine, in device memory so that its CUDA graphs do not depend on them
 struct RunCtl { int run_id, n_ticks, stream_off, stream_ticks; const rlm_tick_msg* stream; long long pad; };

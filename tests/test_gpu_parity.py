@@ -133,6 +133,9 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
     ({"RLM_ENGINE": "s", "RLM_AGENT_VARIANT": "3"}, "sarsa"),  # ... with the round-1 three-warp learner kernel
     ({"RLM_ROUNDS": "1"}, "q_learn"),             # round-paced engine (rlm_env_round_kernel): every env ticks to its step end
     ({"RLM_ROUNDS": "1"}, "double_q_learn"),
+    ({"RLM_ROUNDS": "1", "RLM_ROUND_CAP": "2"}, "q_learn"),   # ... with at most two ticks per env and round
+    ({"RLM_ROUNDS": "1", "RLM_ROUND_CAP": "1", "RLM_ROUND_STREAMS": "2"}, "sarsa"),
+    ({"RLM_ENVW_WARPS": "2"}, "q_learn"),         # two envs per CTA of the warp-per-env tick kernel
 ])
 def test_every_engine_variant_matches_oracle(rlm, oracle, monkeypatch, env_vars, algo):
     """The non-default kernels (selected by environment variables read in rlm_create) are held to the same bar."""
