@@ -44,6 +44,17 @@ WORKLOADS = {
 DRAM_RANDOM_SECTORS_PER_S = 53.6e9
 
 
+def engine_is_rounds(B, algo, shared, ticks_per_call):
+    """Mirrors rlm_create / rlm_run_ticks (rlm_api.cu): the round-paced engine is the default for independent policies on the
+    warp-per-env tick kernel (<= 16384 envs) and run calls of at least 128 ticks; RLM_ROUNDS / RLM_ENGINE override."""
+    if shared or B > 16384 or os.environ.get("RLM_ENV_VARIANT", "0") not in ("0", ""):
+        return False
+    r = os.environ.get("RLM_ROUNDS")
+    if r is not None:
+        return r not in ("0", "")
+    return "RLM_ENGINE" not in os.environ and algo in ("q_learn", "sarsa", "double_q_learn") and ticks_per_call >= 128
+
+
 def workload_string(name, B, algo, M):
     """Identical in the `ours` and `reference` arms (the driver compares it)."""
     return "%s: %d parallel LOBs per GPU, %s + tile coding (32 tilings, memory_size %d per env), synthetic Poisson order flow" % (
@@ -234,8 +245,8 @@ def measure(ctx, name, args, steps, warmup, headline):
     # every tick kernel and every learner kernel (direct launches; rlm_set_profiling) -> the dominant kernel's average
     # launch duration for the roofline block
     kt = None
-    prof_ticks = 0 if (shared and ctx.world > 1) else min(ticks, 128)
-    if prof_ticks > 0 and os.environ.get("RLM_ENGINE", "s")[:1] == "s" and not os.environ.get("RLM_ROUNDS"):
+    prof_ticks = 0 if (shared and ctx.world > 1) else min(ticks, 256)  # (>= 128: the same engine as the timed calls)
+    if prof_ticks > 0 and os.environ.get("RLM_ENGINE", "s")[:1] == "s":
         try:
             m.set_profiling(True)
             cp0 = m.counters()
@@ -265,6 +276,7 @@ def measure(ctx, name, args, steps, warmup, headline):
         achieved = per_gpu * b_step / 1e9
         engine = os.environ.get("RLM_ENGINE", "s")[:1]
         fused = engine == "F" and not shared
+        rounds = engine_is_rounds(B, algo, shared, ticks)
         # DRAM sectors one env step touches at random when the table does not fit on chip: 864 gathers + Z re-reads of
         # updated weights that miss + 2 Z for the read-modify-write of theta (28 Z algorithmic bytes are trace-list traffic)
         sectors = (1728.0 if is_dq else 864.0) + 2.0 * z_bar
@@ -274,13 +286,16 @@ def measure(ctx, name, args, steps, warmup, headline):
             "mean_ticks_per_step": k_bar, "mean_nonzero_traces": z_bar, "ticks_per_s": ticks_all / (total_ms * 1e-3),
             "pretrain_ticks": pretrain, "theta_nonzero_fraction_at_start": occ, "gpu_launches": int(launches),
             "policy": "shared theta, one SUM all-reduce of dtheta per tick" if shared else "independent theta per env, no collective",
+            "engine": ("round-paced (two launches per round; every live env runs up to %s ticks per round, until its step ends)" % os.environ.get("RLM_ROUND_CAP", "3")
+                       if rounds else {"F": "fused persistent kernel (one launch per bench step)"}.get(engine, "tick-synchronous (two launches per market tick)")),
             "l2": ("working set (theta %.1f GB per GPU) is larger than L2; no flush needed" % (B * M * 8 / 1e9)) if not shared
                   else ("shared theta %.0f MB (L2-resident) + %.1f GB of env records, traces and generator state" % (M * 8 / 1e6, B * 8.0e3 / 1e9)),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_nominal_8TBs": achieved / 8000.0, "traffic": None, "peak_source": peak_src,
                 "kernel": ("rlm_fused2_kernel (market ticks + learner steps of all envs, one launch per bench step)" if fused else
-                           "whole tick (env tick kernel + learner kernel, two launches per market tick)"),
+                           ("whole round (tick kernel + learner kernel, two launches per round)" if rounds else
+                            "whole tick (env tick kernel + learner kernel, two launches per market tick)")),
                 "algorithmic_bytes_per_env_step": b_step,
                 "env_steps_per_launch": (steps_all / max(ctx.world, 1)) / max(launches, 1),
                 "avg_launch_ms": total_ms / max(launches, 1) if fused else None,
@@ -297,12 +312,15 @@ def measure(ctx, name, args, steps, warmup, headline):
             # learner kernel: steps x (B_q + 28 Z); tick kernel: envs x (B_msg + B_ring) + steps x 2 S_env
             spl = kt["steps"] / float(kt["agent_launches"])
             zpl = kt["z"] / float(max(kt["steps"], 1))
-            learner = {"kernel": "learner kernel (one launch per market tick: the learner steps of the envs whose midprice moved)",
+            learner = {"kernel": "learner kernel (%s)" % ("one launch per round: the learner steps of the envs whose step ended in the round"
+                                                          if rounds else "one launch per market tick: the learner steps of the envs whose midprice moved"),
                        "avg_launch_ms": kt["agent_ms"] / kt["agent_launches"], "env_steps_per_launch": spl,
                        "algorithmic_bytes_per_launch": spl * ((27648.0 if is_dq else 13824.0) + 28.0 * zpl)}
-            tick = {"kernel": "market tick kernel (one launch per market tick, every env)",
-                    "avg_launch_ms": kt["env_ms"] / kt["env_launches"], "envs_per_launch": B,
-                    "algorithmic_bytes_per_launch": B * 208.0 + spl * 1280.0}
+            tpl = kt["ticks"] * float(B) / kt["env_launches"]  # env ticks per launch
+            tick = {"kernel": "market tick kernel (%s)" % ("one launch per round: every live env runs up to round_cap ticks" if rounds
+                                                           else "one launch per market tick, every env"),
+                    "avg_launch_ms": kt["env_ms"] / kt["env_launches"], "env_ticks_per_launch": tpl,
+                    "algorithmic_bytes_per_launch": tpl * 208.0 + spl * 1280.0}
             for k in (learner, tick):
                 k["achieved"] = k["algorithmic_bytes_per_launch"] / (k["avg_launch_ms"] * 1e-3) / 1e9
                 k["frac"] = k["achieved"] / peak
@@ -398,6 +416,7 @@ def e2e_leg(ctx, m, name, args, shape):
     st = _allreduce(ctx, [cc1.steps - cc0.steps], "SUM")[0]
     return {"value": st / secs, "unit": "env_steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": B * 8,
             "steps": n_steps, "ticks_per_step": ticks, "distinct_streams": distinct,
+            "engine": "round-paced" if engine_is_rounds(B, algo, False, ticks) else "tick-synchronous (run calls of %d ticks return at once, so that the next upload overlaps them)" % ticks,
             "note": "STREAM source: rlm_load_ticks from pinned host memory (double-buffered upload) + rlm_run_ticks + rlm_get_reward per step"}
 
 
@@ -431,8 +450,7 @@ def run_ours(args):
                        "mean_ticks_per_step": res["mean_ticks_per_step"], "mean_nonzero_traces": res["mean_nonzero_traces"],
                        "policy": res["policy"], "l2": res["l2"], "ticks_per_s": res["ticks_per_s"],
                        "flow": "in-kernel generator (device-resident leg); host-generated streams of every env (e2e leg)",
-                       "engine": {"F": "fused persistent kernel (one launch per bench step)", "s": "tick-synchronous (two launches per market tick)"}.get(
-                           os.environ.get("RLM_ENGINE", "s")[:1], os.environ.get("RLM_ENGINE", "")),
+                       "engine": res["engine"],
                        "pretrain_ticks": res["pretrain_ticks"], "theta_nonzero_fraction_at_start": res["theta_nonzero_fraction_at_start"],
                        "state": "timed after %d ticks of training per env: long-run weight tables" % res["pretrain_ticks"]},
             "gpu_launches": res["gpu_launches"], "clocks": res.get("clocks"), "roofline": res["roofline"],

@@ -78,7 +78,8 @@ struct rlm_handle_s {
   cudaStream_t sub_stream[RLM_MAX_SUB] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[RLM_MAX_SUB] = {};
   // round-paced engine (independent policies, warp-per-env ticks): see run_rounds
-  bool rounds = false;
+  bool rounds = false;       // forced (RLM_ROUNDS=1)
+  bool rounds_auto = false;  // default: run calls of at least RLM_ROUNDS_MIN_TICKS ticks
   int run_seq = 0;
   int round_streams = 1;  // sub-batches of the round-paced engine, each on its own stream (RLM_ROUND_STREAMS)
   int* h_live = nullptr;  // pinned [RLM_MAX_SUB][2]: ready count of the last round of each group in flight
@@ -223,9 +224,10 @@ static int derive(rlm_handle_s* h) {
   // ---- venue chains (src/market/market.cpp:27-37, 78-128), same fp64 operation order as the reference
   VenueD& v = p.venue;
   v.n = c.n_bands;
-  for (int i = 0; i < RLM_MAX_BANDS; ++i) { v.px[i] = INFINITY; v.ts[i] = 1.0; v.tts_tick[i] = INT_MAX; }
+  for (int i = 0; i < RLM_MAX_BANDS; ++i) { v.px[i] = INFINITY; v.ts[i] = 1.0; v.inv_ts[i] = 0.0; v.tts_tick[i] = INT_MAX; }
   for (int i = 0; i < c.n_bands; ++i) {
     v.px[i] = c.band_px[i]; v.ts[i] = c.band_ts[i];
+    { int ex = 0; if (frexp(c.band_ts[i], &ex) == 0.5) v.inv_ts[i] = 1.0 / c.band_ts[i]; }  // power of two: exact reciprocal
     if (i > 0 && !(c.band_px[i] > c.band_px[i - 1])) return fail(RLM_ERR_INVALID_ARGUMENT, "venue bands must ascend");
     if (!(c.band_ts[i] > 0)) return fail(RLM_ERR_INVALID_ARGUMENT, "venue tick sizes must be positive");
   }
@@ -436,11 +438,21 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
     // warp-per-env ticks minimise latency (small batches); thread-per-env ticks are ~2x cheaper in issue slots
     h->env_variant = (cfg->n_envs > 16384) ? 1 : 0;
     if (const char* s = getenv("RLM_ENV_VARIANT")) h->env_variant = atoi(s) ? 1 : 0;
-    // the round-paced engine (RLM_ROUNDS=1) needs envs that never interact and the warp-per-env tick kernel.  Off by
-    // default: measured on B200 at C1 it is parity-green but slower than the tick-synchronous pair (8.9e6 env steps/s
-    // on one stream, 1.03e7 on eight, against 1.17e7) -- profiles/r2_round_engine.txt
+    // The round-paced engine needs envs that never interact and the warp-per-env tick kernel.  With a cap on the ticks
+    // an env runs per round (RLM_ROUND_CAP, default 3) it is the faster engine for long run calls: measured on B200 at
+    // C1, 1.32e7 env steps/s against 1.22e7 for the tick-synchronous pair (a round hands the learner kernel ~2 700 steps
+    // instead of ~1 200 and pays the two launch gaps once per 2.2 ticks).  Without a cap the round waits for the env
+    // with the longest run of unchanged midprices: 0.97e7.  Short calls stay tick-synchronous: a call ends with a tail
+    // of thinly populated rounds (envs drift apart by a few ticks), which only a long call amortises, and the
+    // round-paced call returns only when the device is nearly done (no overlap with the next chunk's upload).
+    // RLM_ROUNDS=1 forces it for every call, RLM_ROUNDS=0 (or an explicit RLM_ENGINE) switches it off.
     h->rounds = false;
-    if (const char* s = getenv("RLM_ROUNDS")) h->rounds = atoi(s) != 0 && !cfg->shared_policy && h->env_variant == 0;
+    h->rounds_auto = !cfg->shared_policy && h->env_variant == 0 && h->engine == 1 && !getenv("RLM_ENGINE") && cfg->algorithm < RLM_ALGO_R_LEARN;
+    if (const char* s = getenv("RLM_ROUNDS")) {
+      h->rounds = atoi(s) != 0 && !cfg->shared_policy && h->env_variant == 0;
+      h->rounds_auto = false;
+    }
+    if (!getenv("RLM_ROUND_CAP")) h->dyn.round_cap = 3;
     if (const char* s = getenv("RLM_PDL")) rlm_set_pdl(atoi(s));  // programmatic dependent launch of the per-tick kernels (default off: slower when measured)
     if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
   }
@@ -569,6 +581,7 @@ int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks) {
 
 static int run_ticks_impl(rlm_handle h, int32_t n_ticks);
 static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks);
+#define RLM_ROUNDS_MIN_TICKS 128
 
 int rlm_run_ticks(rlm_handle h, int32_t n_ticks) {
   API_LOCK;
@@ -597,7 +610,7 @@ static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
   CK(rlm_launch_runctl(h->ptr, rc, h->stream));
   // sub-batches on their own streams: the learner kernel of one (throughput-bound: more steps than resident warps)
   // runs while the tick kernel of another (latency-bound: a few serial ticks per env) does
-  const int S = std::max(1, std::min(h->round_streams, (B + 255) / 256));
+  const int S = h->profile ? 1 : std::max(1, std::min(h->round_streams, (B + 255) / 256));
   int sub0[RLM_MAX_SUB + 1];
   {
     const int per = (((B + S - 1) / S) + 31) & ~31;
@@ -605,8 +618,9 @@ static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
   }
   int G = n_ticks >= 512 ? 32 : (n_ticks >= 128 ? 16 : 8);
   G = std::min(std::min(G, n_ticks + 1), h->ready_cap);
-  const bool graphs = h->use_graphs && h->graph_warm;
+  const bool graphs = h->use_graphs && h->graph_warm && !h->profile;
   h->graph_warm = true;  // (the first call launches directly: function attributes are set outside any capture)
+  if (h->profile) while ((int)h->ev.size() < 3 * G) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev.push_back(e); }
   DynParams dts[RLM_MAX_SUB];
   DevPtrs pss[RLM_MAX_SUB];
   cudaGraphExec_t exec[RLM_MAX_SUB] = {};
@@ -662,8 +676,24 @@ static int run_rounds(rlm_handle h, const DynParams& d, int n_ticks) {
         CK(cudaMemsetAsync(pss[s].ready_count, 0, (size_t)G * 4, st));
         CK(cudaMemsetAsync(pss[s].ready_count + RLM_LIVE_OFF, 0, (size_t)G * 4, st));
         for (int r = 0; r < G; ++r) {
+          if (h->profile) CK(cudaEventRecord(h->ev[3 * r], st));
           CK(rlm_launch_env_round(pss[s], dts[s], dts[s].n_sub, r, st));
+          if (h->profile) CK(cudaEventRecord(h->ev[3 * r + 1], st));
           CK(launch_agent_on(h, pss[s], dts[s], r, 0, st));
+          if (h->profile) CK(cudaEventRecord(h->ev[3 * r + 2], st));
+        }
+        if (h->profile) {  // bench instrumentation: per-kernel times of the rounds that had work (S == 1, direct launches)
+          std::vector<int> cnt(2 * G);
+          CK(cudaStreamSynchronize(st));
+          CK(cudaMemcpy(cnt.data(), pss[s].ready_count, (size_t)G * 4, cudaMemcpyDeviceToHost));
+          CK(cudaMemcpy(cnt.data() + G, pss[s].ready_count + RLM_LIVE_OFF, (size_t)G * 4, cudaMemcpyDeviceToHost));
+          for (int r = 0; r < G; ++r) {
+            float a = 0, b = 0;
+            CK(cudaEventElapsedTime(&a, h->ev[3 * r], h->ev[3 * r + 1]));
+            CK(cudaEventElapsedTime(&b, h->ev[3 * r + 1], h->ev[3 * r + 2]));
+            if (cnt[G + r] > 0) { h->prof_env_ms += a; h->prof_env_launches++; }
+            if (cnt[r] > 0) { h->prof_agent_ms += b; h->prof_agent_launches++; }
+          }
         }
       }
       h->launches += 2 * G;
@@ -731,7 +761,8 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
     h->launches += 1;
     return RLM_OK;
   }
-  if (h->rounds && h->engine == 1 && !d.backtest && !d.hold && !h->profile && h->n_sub <= 1) return run_rounds(h, d, n_ticks);
+  if ((h->rounds || (h->rounds_auto && n_ticks >= RLM_ROUNDS_MIN_TICKS)) && h->engine == 1 && !d.backtest && !d.hold && h->n_sub <= 1)
+    return run_rounds(h, d, n_ticks);
   // two kernels per tick (env tick, then the learner step of the envs whose midprice moved), then one
   // trailing env pass that only runs the pending action selections, so that the observable state
   // after the call is "every env sits inside performAction's loop".  With n_sub > 1 every sub-batch does this on its own

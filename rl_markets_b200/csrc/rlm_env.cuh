@@ -36,13 +36,23 @@ static_assert((RLM_MAX_BANDS & (RLM_MAX_BANDS - 1)) == 0, "the band search halve
 // Market::ToTicks (market.cpp:78-102).  Bands below the one containing `price` contribute a
 // price-independent chain of truncating `int += double` steps, precomputed on the host
 // (VenueD::cum_full); the loop below is the reference loop entered at that band.
-__device__ __noinline__ int to_ticks(double price, int* err) {
+// band_hint (optional): in/out, the band of the caller's previous conversion -- prices stay inside one band for hours, so
+// two comparisons usually replace the five dependent look-ups of the search.  A band whose tick size is a power of two
+// (VenueD::inv_ts != 0) is divided by multiplying with the exact reciprocal: the same IEEE result without the fp64
+// division sequence.
+__device__ __noinline__ int to_ticks(double price, int* err, int* band_hint = nullptr) {
   const VenueD& V = P.venue;
   if (price < V.px[0]) { *err |= ERR_TICK_RANGE; return 0; }
-  int k = 0;  // band containing price = last band start <= price; binary search (px[i >= n] = +inf, px[0] <= price)
+  int k = 0;  // band containing price = last band start <= price (px[i >= n] = +inf, px[0] <= price)
+  const int hk = band_hint ? *band_hint : -1;
+  if ((unsigned)hk < (unsigned)(RLM_MAX_BANDS - 1) && !(price < V.px[hk]) && price < V.px[hk + 1]) {
+    k = hk;
+  } else {  // binary search
 #pragma unroll
-  for (int step = RLM_MAX_BANDS / 2; step >= 1; step >>= 1)
-    if (!(price < V.px[k + step])) k += step;
+    for (int step = RLM_MAX_BANDS / 2; step >= 1; step >>= 1)
+      if (!(price < V.px[k + step])) k += step;
+    if (band_hint) *band_hint = k;
+  }
   int ticks = V.cum_full[k];
   double tsp = V.ts[k];  // tick_size(price) = band containing price (market.cpp:130-138)
   int it = k;
@@ -51,7 +61,9 @@ __device__ __noinline__ int to_ticks(double price, int* err) {
     double ub;
     if (it == V.n - 1 || price < V.px[it + 1]) ub = price + tsp / 2.0;
     else ub = V.px[it + 1];
-    ticks = (int)((double)ticks + (ub - V.px[it]) / V.ts[it]);  // int += double
+    const double inv = V.inv_ts[it];
+    const double q = (inv != 0.0) ? (ub - V.px[it]) * inv : (ub - V.px[it]) / V.ts[it];
+    ticks = (int)((double)ticks + q);  // int += double
     ++it;
   }
   return ticks;
@@ -384,12 +396,12 @@ __device__ __noinline__ void clear_inventory(EnvHdr& e) {
 __device__ __noinline__ void place_orders(EnvHdr& e, int al, int bl) {
   e.ask_level = al; e.bid_level = bl;
   if (P.l2p_book) {
-    e.ask_quote = to_price(to_ticks(e.side[0].px[0], &e.err) + al, &e.err);
-    e.bid_quote = to_price(to_ticks(e.side[1].px[0], &e.err) - bl, &e.err);
+    e.ask_quote = to_price(to_ticks(e.side[0].px[0], &e.err, &e.tk_band) + al, &e.err);
+    e.bid_quote = to_price(to_ticks(e.side[1].px[0], &e.err, &e.tk_band) - bl, &e.err);
   } else {
     double tp = e.tp_val, half_spd = fmax(0.0, e.w_mean[W_SPREAD] / 2.0);
-    e.ask_quote = to_price(to_ticks(tp + (double)al * half_spd, &e.err), &e.err);
-    e.bid_quote = to_price(to_ticks(tp - (double)bl * half_spd, &e.err), &e.err);
+    e.ask_quote = to_price(to_ticks(tp + (double)al * half_spd, &e.err, &e.tk_band), &e.err);
+    e.bid_quote = to_price(to_ticks(tp - (double)bl * half_spd, &e.err, &e.tk_band), &e.err);
   }
   side_replace_order(e.side[0], e.ask_quote, P.order_size, &e.err);
   side_replace_order(e.side[1], e.bid_quote, P.order_size, &e.err);
@@ -453,7 +465,7 @@ __device__ __noinline__ void next_state_tail(EnvHdr& e, const Fill& au, const Fi
   // (memo: ToTicks is a pure function of the price; a zero-initialised memo can only match mid == 0, which is recomputed)
   long long mpt;
   if (mid == e.tk_px && mid > 0.0) mpt = e.tk_ticks;
-  else { const int t = to_ticks(mid, &e.err); mpt = t; e.tk_px = mid; e.tk_ticks = t; }
+  else { const int t = to_ticks(mid, &e.err, &e.tk_band); mpt = t; e.tk_px = mid; e.tk_ticks = t; }
   double mpm = mid - m_last_midprice(e), sp = m_spread(e);
   pushv[W_MID] = (double)mpt;
   pushv[W_VLT] = (double)mpt;
@@ -573,16 +585,37 @@ __device__ __forceinline__ double ulb_ref(double val, double lb, double ub) {
   return (m < lb) ? lb : m;
 }
 
+// The state variables that convert two prices to ticks (spd, mpm, a_dist, b_dist), split so that the lanes of the
+// warp-per-env tick kernel run their Market::ToTicks calls together instead of one switch case after the other.
+// var_tick_args: the two prices (returns false for every other variable, and for a dist variable without a live order);
+// var_from_ticks: the variable from the two tick counts -- the same expressions as in get_variable below.
+__device__ __forceinline__ bool var_tick_args(const EnvHdr& e, const double* ring, int v, double& x0, double& x1) {
+  switch (v) {
+    case RLM_VAR_SPD: x0 = e.side[0].px[0]; x1 = e.side[1].px[0]; return true;
+    case RLM_VAR_MPM: x0 = win_front(e, ring, W_MID); x1 = win_back(e, ring, W_MID); return true;
+    case RLM_VAR_A_DIST: if (!e.side[0].ord.live) return false; x0 = e.side[0].ord.price; x1 = e.side[0].px[0]; return true;
+    case RLM_VAR_B_DIST: if (!e.side[1].ord.live) return false; x0 = e.side[1].px[0]; x1 = e.side[1].ord.price; return true;
+  }
+  return false;
+}
+__device__ __forceinline__ double var_from_ticks(int v, int t0, int t1) {
+  switch (v) {
+    case RLM_VAR_SPD: return ulb_ref((double)(t0 - t1), 0.0, 20.0);
+    case RLM_VAR_MPM: return ulb_ref((double)(t0 - t1), -10.0, 10.0);
+  }
+  return (double)t0 - (double)t1;  // a_dist / b_dist
+}
+
 // Intraday::getVariable (intraday.cpp:315-409)
 __device__ __noinline__ double get_variable(EnvHdr& e, const double* ring, int v) {
   switch (v) {
     case RLM_VAR_POS: return (double)e.position / (double)P.order_size;
     case RLM_VAR_SPD: {
-      double d = (double)(to_ticks(e.side[0].px[0], &e.err) - to_ticks(e.side[1].px[0], &e.err));
+      double d = (double)(to_ticks(e.side[0].px[0], &e.err, &e.tk_band) - to_ticks(e.side[1].px[0], &e.err, &e.tk_band));
       return ulb_ref(d, 0.0, 20.0);
     }
     case RLM_VAR_MPM: {
-      double d = (double)(to_ticks(win_front(e, ring, W_MID), &e.err) - to_ticks(win_back(e, ring, W_MID), &e.err));
+      double d = (double)(to_ticks(win_front(e, ring, W_MID), &e.err, &e.tk_band) - to_ticks(win_back(e, ring, W_MID), &e.err, &e.tk_band));
       return ulb_ref(d, -10.0, 10.0);
     }
     case RLM_VAR_IMB: {
@@ -603,7 +636,7 @@ __device__ __noinline__ double get_variable(EnvHdr& e, const double* ring, int v
       return ulb_ref(d / e.w_mean[W_SPREAD], -10.0, 10.0);
     }
     case RLM_VAR_A_DIST:
-      if (e.side[0].ord.live) return ((double)to_ticks(e.side[0].ord.price, &e.err) - (double)to_ticks(e.side[0].px[0], &e.err));
+      if (e.side[0].ord.live) return ((double)to_ticks(e.side[0].ord.price, &e.err, &e.tk_band) - (double)to_ticks(e.side[0].px[0], &e.err, &e.tk_band));
       else return -100.0;
     case RLM_VAR_A_QUEUE:
       if (e.side[0].ord.live) {
@@ -611,7 +644,7 @@ __device__ __noinline__ double get_variable(EnvHdr& e, const double* ring, int v
         return 10.0 * (double)(long long)qp;                                                        // book.cpp:351-357
       } else return -1.0;
     case RLM_VAR_B_DIST:
-      if (e.side[1].ord.live) return ((double)to_ticks(e.side[1].px[0], &e.err) - (double)to_ticks(e.side[1].ord.price, &e.err));
+      if (e.side[1].ord.live) return ((double)to_ticks(e.side[1].px[0], &e.err, &e.tk_band) - (double)to_ticks(e.side[1].ord.price, &e.err, &e.tk_band));
       else return -100.0;
     case RLM_VAR_B_QUEUE:
       if (e.side[1].ord.live) {

@@ -269,6 +269,71 @@ __device__ __forceinline__ bool begin_step(EnvHdr& e, unsigned long long* mt_pol
   begin_apply(e, a);
   return true;
 }
+// The same for the warp-per-env tick kernels: lane 0 selects the action and runs DoAction's book-keeping, the two quotes
+// (Intraday::l2p_ + RiskManager::PlaceOrder, intraday.cpp:64-82,163-173) are priced and placed by lane 0 (ask) and lane 1
+// (bid) side by side -- two ToTicks / ToPrice / queue look-ups instead of four in a row on the launch's critical path.
+__device__ __forceinline__ void begin_step_warp(EnvHdr& e, unsigned long long* mt_pol, const DynParams& D, int* flag, int lane) {
+  if (lane == 0) {
+    int a;
+    if (e.ag.kind == 4) a = e.ag.cur_action;  // (rlm_act already drew the action)
+    else a = begin_select(e, mt_pol, D);
+    int place = 0;
+    if (a >= 0) {
+      e.ag.cur_action = a;
+      e.last_action = a;
+      e.lo_vol_step = 0;
+      e.pnl_step = 0.0;
+      e.momentum_pnl_step = 0.0;
+      int al = 0, bl = 0;
+      place = 1;
+      switch (a) {  // Intraday::DoAction (intraday.cpp:175-220), see do_action
+        case 0: al = 1; bl = 1; break;
+        case 1: clear_inventory(e); al = e.ask_level; bl = e.bid_level; break;
+        case 2: al = 2; bl = 2; break;
+        case 3: al = 3; bl = 3; break;
+        case 4: al = 0; bl = 2; break;
+        case 5: al = 2; bl = 0; break;
+        case 6: al = 1; bl = 4; break;
+        case 7: al = 4; bl = 1; break;
+        case 8: al = 5; bl = 5; break;
+        default: place = 0; break;
+      }
+      if (place) { e.ask_level = al; e.bid_level = bl; }
+    }
+    flag[0] = a;
+    flag[1] = place;
+  }
+  __syncwarp();
+  const int a = flag[0];
+  if (a >= 0) {
+    if (flag[1] && lane < 2) {  // place_orders, one side per lane
+      int lerr = 0, hint = e.tk_band;
+      const int lv = lane == 0 ? e.ask_level : -e.bid_level;
+      double q;
+      if (P.l2p_book) {
+        q = to_price(to_ticks(e.side[lane].px[0], &lerr, &hint) + lv, &lerr);
+      } else {
+        const double tp = e.tp_val, half_spd = fmax(0.0, e.w_mean[W_SPREAD] / 2.0);
+        const double px = lane == 0 ? tp + (double)e.ask_level * half_spd : tp - (double)e.bid_level * half_spd;
+        q = to_price(to_ticks(px, &lerr, &hint), &lerr);
+      }
+      if (lane == 0) e.ask_quote = q; else e.bid_quote = q;
+      side_replace_order(e.side[lane], q, P.order_size, &lerr);
+      if (lerr) atomicOr(&e.err, lerr);
+    }
+    __syncwarp();
+    if (lane == 0) {  // rest of begin_apply
+      check_orders(e);
+      update_stats(e);
+      e.agg_r = get_reward(e);
+      e.agg_pnl = e.pnl_step;
+      e.agg_mpm = 0.0;
+      e.ag.kind = 3;
+    }
+  }
+  if (lane == 0) e.ag.need_begin = 0;
+  __syncwarp();
+}
 // split surface: is this env waiting for rlm_agent_update (its step or its warm-up has ended) or for rlm_env_step to
 // apply an action?  Such envs do not tick under DynParams::hold.
 __device__ __forceinline__ bool env_on_hold(const EnvHdr& e) {
@@ -339,12 +404,100 @@ cudaError_t rlm_launch_step_out(const DevPtrs& ptr, int n_envs, double* reward, 
 __device__ __noinline__ void flow_next_dev(rlm_flow_state* s, rlm_tick_msg* m) {
   rlm_flow_next(s, &P.flow, rlm_flow_skellam20_lut, rlm_flow_pois30_lut, rlm_flow_pois1p5_lut, m);
 }
-// warp version: lanes 0..2 evaluate the three Philox calls, lane 0 applies them
+// warp version of rlm_flow_next (include/rlm_flow.h): lanes 0..2 evaluate the three Philox calls; the book part of
+// rlm_flow_apply runs one LEVEL per lane -- lanes 0..4 = ask levels, 5..9 = bid levels: the shift of the level volumes, the
+// Skellam add/cancel draw, the level's price and its slot in the message -- and the prints one PRICE per lane (lanes
+// 0..3 = bid-1, bid, ask, ask+1).  Same integer arithmetic as the host function, statement by statement; the generated
+// stream is compared with the host's bit for bit (tests/test_gpu_parity.py::test_stream_mode_equals_generator_mode).
+__device__ __forceinline__ uint32_t flow_fresh3(uint32_t f0, uint32_t f1, uint32_t f2, int i) { return i == 0 ? f0 : (i == 1 ? f1 : f2); }
 __device__ __noinline__ void flow_next_warp(rlm_flow_state* s, rlm_tick_msg* m, unsigned* r12 /* 12 words of shared memory */, int lane) {
   if (lane < 3) rlm_flow_draw(s, (uint32_t)lane, r12 + 4 * lane);
   __syncwarp();
-  if (lane == 0)
-    rlm_flow_apply(s, &P.flow, rlm_flow_skellam20_lut, rlm_flow_pois30_lut, rlm_flow_pois1p5_lut, r12, r12 + 4, r12 + 8, m);
+  const rlm_flow_params* p = &P.flow;
+  const uint32_t* r0 = r12;
+  const uint32_t* r1 = r12 + 4;
+  const uint32_t* r2 = r12 + 8;
+  const int32_t tick = s->tick, bid_tick = s->bid_tick, spread = s->spread;
+  // ---- prints against the PRE-update book: lane j < 4 sums the prints that land on price j (ascending price)
+  const int32_t pa = bid_tick + spread, pb = bid_tick;
+  const int n_prints = (tick == 0) ? 0 : (int)rlm_flow_pois1p5_lut[(r0[0] >> 24) & 0xFFu];
+  int32_t agg = 0;
+  if (lane < 4) {
+#pragma unroll 1
+    for (int i = 0; i < n_prints; ++i) {
+      const uint32_t bits = (r0[1] >> (12 + 3 * i)) & 7u;
+      const uint32_t u12 = (i < 2) ? ((r2[1] >> (12 * i)) & 0xFFFu) : ((r2[2] >> (12 * (i - 2))) & 0xFFFu);
+      const int deep = ((int)(bits >> 1) < p->p_deep_u2) ? 1 : 0;
+      const int slot = (bits & 1u) ? 2 + deep : 1 - deep;
+      if (slot == lane) agg += 1 + (int32_t)rlm_flow_pois30_lut[u12];
+    }
+  }
+  const unsigned txm = __ballot_sync(FULL, lane < 4 && agg > 0);
+  // ---- evolve the book (not on the very first row): every lane derives the scalars, lanes 0..9 own one level each
+  int move = 0, new_spread = spread;
+  const bool evolve = tick > 0;
+  if (evolve) {
+    const uint32_t um = r0[0] & 0xFFFu;
+    if ((int32_t)um < p->p_move_u12 / 2) move = -1;
+    else if ((int32_t)um < p->p_move_u12) move = +1;
+    if ((int32_t)((r0[0] >> 12) & 0xFFFu) < p->p_spread_u12) {
+      const uint32_t us = r0[1] & 0xFFFu;
+      new_spread = ((int32_t)us < p->spread_c1_u12) ? 1 : (((int32_t)us < p->spread_c2_u12) ? 2 : 3);
+    }
+    if (bid_tick + move - (RLM_DEPTH - 1) < p->tick_lo) move = +1;
+    if (bid_tick + move + new_spread + (RLM_DEPTH - 1) > p->tick_hi) move = -1;
+  }
+  const int32_t new_bid = bid_tick + move;
+  const bool is_bid = lane >= RLM_DEPTH;
+  const int l = is_bid ? lane - RLM_DEPTH : lane;
+  int32_t v = 0;
+  if (lane < 2 * RLM_DEPTH) {
+    const int32_t* vol = is_bid ? s->bid_vol : s->ask_vol;
+    v = vol[l];
+    if (evolve) {
+      // rlm_flow_shift: bid best moves by `move` (d = -move), ask best by move + (new_spread - spread) (d = +shift)
+      const int d = is_bid ? -move : move + (new_spread - spread);
+      const uint32_t f0 = is_bid ? (r0[3] >> 16) : (r0[2] & 0xFFFFu);
+      const uint32_t f1 = is_bid ? ((r0[3] >> 8) & 0xFFFFu) : (r0[2] >> 16);
+      const uint32_t f2 = is_bid ? ((r0[2] >> 8) & 0xFFFFu) : (r0[3] & 0xFFFFu);
+      if (d > 0) {
+        const int src = l + d;
+        v = (src < RLM_DEPTH) ? vol[src] : (int32_t)(100u + flow_fresh3(f0, f1, f2, (l + d - RLM_DEPTH) % 3) % 800u);
+      } else if (d < 0) {
+        const int src = l + d;
+        v = (src >= 0) ? vol[src] : (int32_t)(100u + flow_fresh3(f0, f1, f2, l % 3) % 800u);
+      }
+      // depth add - cancel per level: draws 0..4 ask, 5..9 bid
+      const uint32_t w = (lane < 8) ? r1[lane >> 1] : r2[0];
+      const uint32_t u = (lane & 1) ? ((w >> 12) & 0xFFFu) : (w & 0xFFFu);
+      v += (int32_t)rlm_flow_skellam20_lut[u];
+      v = v < 1 ? 1 : v;
+    }
+  }
+  __syncwarp();  // every lane has read the old level volumes and the old state scalars
+  if (lane < 2 * RLM_DEPTH) {
+    if (is_bid) { s->bid_vol[l] = v; m->bid_vol[l] = v; m->bid_px[l] = rlm_flow_px(p, new_bid - l); }
+    else { s->ask_vol[l] = v; m->ask_vol[l] = v; m->ask_px[l] = rlm_flow_px(p, new_bid + new_spread + l); }
+  }
+  if (lane < RLM_N_TX_MAX) {  // aggregated prints, ascending price, compacted: {pb - 1, pb, pa, pa + 1}
+    const int32_t agg_tick = lane == 0 ? pb - 1 : (lane == 1 ? pb : (lane == 2 ? pa : pa + 1));
+    const int n_tx = __popc(txm);
+    if (agg > 0) {
+      const int pos = __popc(txm & ((1u << lane) - 1u));
+      m->tx_px[pos] = rlm_flow_px(p, agg_tick);
+      m->tx_vol[pos] = agg;
+    }
+    if (lane >= n_tx) { m->tx_px[lane] = 0.0f; m->tx_vol[lane] = 0; }
+    if (lane == 0) {
+      m->n_tx = n_tx;
+      m->time_ms = p->t0_ms + (tick + 1) * p->dt_ms;
+      m->date = p->date;
+      m->flags = 0;
+      s->bid_tick = new_bid;
+      s->spread = new_spread;
+      s->tick = tick + 1;
+    }
+  }
 }
 
 // One market tick of one env (thread-per-env).  Returns -1, or the ready kind: 0 = a learner step
@@ -643,8 +796,20 @@ __device__ __forceinline__ int envw_tick(const EnvWarp& w, double* ring, const D
     if (ready == 0) {
       if (lane == W_PNLUP || lane == W_PNLDN) window_push(e, ring, lane, pushv[lane], oldv[lane]);
       __syncwarp();
-      // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane
-      if (lane < P.n_state_vars) e.ag.to_vars[lane] = (float)get_variable(e, ring, P.state_vars[lane]);
+      // State::newState -> Intraday::getState (state.cpp:35-43, intraday.cpp:411-416): one variable per lane.  The
+      // variables built from two Market::ToTicks conversions (spd, mpm, a_dist, b_dist) make those calls together, in
+      // two convergent passes, instead of eight calls one switch case after the other (this is the critical path of the
+      // launch: the warps whose step ends are the last ones to finish)
+      {
+        const bool has = lane < P.n_state_vars;
+        const int var = has ? P.state_vars[lane] : -1;
+        double x0 = 0.0, x1 = 0.0;
+        const bool two = has && var_tick_args(e, ring, var, x0, x1);
+        int t0 = 0, t1 = 0, lerr = 0, hint = e.tk_band;
+        if (two) { t0 = to_ticks(x0, &lerr, &hint); t1 = to_ticks(x1, &lerr, &hint); }
+        if (lerr) atomicOr(&e.err, lerr);
+        if (has) e.ag.to_vars[lane] = (float)(two ? var_from_ticks(var, t0, t1) : get_variable(e, ring, var));
+      }
       if (lane == 31) { e.ag.last_reward = get_reward(e); e.ag.kind = 0; }
       if (D.env_hash && !D.backtest && !P.shared_policy && P.algorithm < RLM_ALGO_R_LEARN) {
         // OPTIONAL (RLM_ENV_HASH=1; off by default): hash the to-state here -- 31 lanes of this warp idle anyway -- hand
@@ -700,10 +865,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   if (D.hold && env_on_hold(e)) return;
   int ready = -1;
   unsigned ticked = 0;
-  if (e.ag.need_begin) {
-    if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
-    __syncwarp();
-  }
+  if (e.ag.need_begin) begin_step_warp(e, ptr.mt_pol + (size_t)env * 312, D, w.flag, lane);
   if (!only_begin && e.phase != PH_DONE) ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, D.stream_ticks, lane, ticked);
   __syncwarp();
   envw_stage_out(g, &e, lane);
@@ -755,10 +917,7 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32, 4) rlm_env_round_kernel(DevPt
   int n_run = 0;
 #pragma unroll 1
   for (;;) {
-    if (e.ag.need_begin) {
-      if (lane == 0) { begin_step(e, ptr.mt_pol + (size_t)env * 312, D); e.ag.need_begin = 0; }
-      __syncwarp();
-    }
+    if (e.ag.need_begin) begin_step_warp(e, ptr.mt_pol + (size_t)env * 312, D, w.flag, lane);
     if (e.phase == PH_DONE || pos >= rc.n_ticks || n_run >= cap) break;
     ready = envw_tick(w, ring, pt, D, env, rc.stream_off + pos, rc.stream_ticks, lane, ticked);
     ++pos; ++n_run;

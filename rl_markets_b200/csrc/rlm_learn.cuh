@@ -39,10 +39,9 @@ __host__ __device__ inline size_t ln_v_bytes(int is_double) { return (size_t)(is
 #endif
 #define UT_SLOTS (1 << UT_LOG2)
 #define UT_MAX_ENTRIES (UT_SLOTS / 2)
-// learner scratch of one step: [V][tile table 4096][update table 8192][tile indices 27 x 32 ints][q_pre 2*9 doubles][dec 6 doubles]
-#define LN_IDX_BYTES (3 * RLM_MAX_ACTIONS * 32 * 4)
+// learner scratch of one step: [V][tile table 4096][update table 8 * UT_SLOTS][q_pre 2*9 doubles][dec 6 doubles]
 __host__ __device__ inline size_t ln_scratch_bytes(int is_double) {
-  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + LN_IDX_BYTES + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
+  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
 }
 // per-warp shared memory of rlm_learn_kernel: [AgentD 704][scratch]
 __host__ __device__ inline size_t ln_warp_bytes(int is_double) { return (size_t)LN_AG_BYTES + ln_scratch_bytes(is_double); }
@@ -50,22 +49,14 @@ static_assert(sizeof(AgentD) <= LN_AG_BYTES, "agent block outgrew its shared-mem
 
 // ---- gathers K0 .. K0+N-1 (k = g*9 + a) of one table in flight together; raw weights -> V[a][g*32 + lane]
 template <int K0, int N>
-__device__ __forceinline__ void ln_gather_issue(const double* __restrict__ th, const LnSums& h, double* v, int* idx = nullptr, int lane = 0) {
+__device__ __forceinline__ void ln_gather_issue(const double* __restrict__ th, const LnSums& h, double* v) {
   const int A = P.n_actions;
   if (P.m_pow2) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const int f = ln_tile<true>(h, K0 + k);
-      v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + f) : 0.0;
-      if (idx) idx[(K0 + k) * 32 + lane] = f;
-    }
+    for (int k = 0; k < N; ++k) v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + ln_tile<true>(h, K0 + k)) : 0.0;
   } else {
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const int f = ln_tile<false>(h, K0 + k);
-      v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + f) : 0.0;
-      if (idx) idx[(K0 + k) * 32 + lane] = f;
-    }
+    for (int k = 0; k < N; ++k) v[k] = (((K0 + k) % RLM_MAX_ACTIONS) < A) ? __ldcg(th + ln_tile<false>(h, K0 + k)) : 0.0;
   }
 }
 template <int K0, int N>
@@ -76,17 +67,16 @@ __device__ __forceinline__ void ln_gather_store(const double* v, int lane, doubl
     if (((K0 + k) % RLM_MAX_ACTIONS) < A) V[((K0 + k) % RLM_MAX_ACTIONS) * LN_VROW + ((K0 + k) / RLM_MAX_ACTIONS) * 32 + lane] = v[k];
 }
 template <bool DBL, int GB>
-__device__ __forceinline__ void ln_gather(const double* __restrict__ th_a, const double* __restrict__ th_b, const LnSums& h, int lane, double* V,
-                                          int* idx = nullptr) {
+__device__ __forceinline__ void ln_gather(const double* __restrict__ th_a, const double* __restrict__ th_b, const LnSums& h, int lane, double* V) {
   static_assert(GB == 27 || GB == 9, "gather batch: everything, or one feature group at a time");
   double v[GB];
   if (GB == 27) {
-    ln_gather_issue<0, GB>(th_a, h, v, idx, lane); ln_gather_store<0, GB>(v, lane, V);
+    ln_gather_issue<0, GB>(th_a, h, v); ln_gather_store<0, GB>(v, lane, V);
     if (DBL) { ln_gather_issue<0, GB>(th_b, h, v); ln_gather_store<0, GB>(v, lane, V + RLM_MAX_ACTIONS * LN_VROW); }
   } else {
-    ln_gather_issue<0, 9>(th_a, h, v, idx, lane); ln_gather_store<0, 9>(v, lane, V);
-    ln_gather_issue<9, 9>(th_a, h, v, idx, lane); ln_gather_store<9, 9>(v, lane, V);
-    ln_gather_issue<18, 9>(th_a, h, v, idx, lane); ln_gather_store<18, 9>(v, lane, V);
+    ln_gather_issue<0, 9>(th_a, h, v); ln_gather_store<0, 9>(v, lane, V);
+    ln_gather_issue<9, 9>(th_a, h, v); ln_gather_store<9, 9>(v, lane, V);
+    ln_gather_issue<18, 9>(th_a, h, v); ln_gather_store<18, 9>(v, lane, V);
     if (DBL) {
       double* Vb = V + RLM_MAX_ACTIONS * LN_VROW;
       ln_gather_issue<0, 9>(th_b, h, v); ln_gather_store<0, 9>(v, lane, Vb);
@@ -109,10 +99,12 @@ __device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every 
   while (atomicCAS(&ut[slot], HS_EMPTY, f) != HS_EMPTY) slot = (slot + 1) & (UT_SLOTS - 1);
   ((float*)(ut + UT_SLOTS))[slot] = ev;
 }
-// idx: this step's 27 x 32 tile indices (row k = g*9 + a, column = lane), stored by the gather
-__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const int* idx, int lane, double* V) {
+// the step's tile indices are re-derived from the hash sums (two instructions each for a power-of-two M): no index table
+__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
   const int A = P.n_actions;
   const float* uv = (const float*)(ut + UT_SLOTS);
+  const bool pow2 = P.m_pow2 != 0;
+  const unsigned mask = (unsigned)(P.memory_size - 1);
   // rolled over the actions (this runs once per step: code size is time), the three feature groups of one action side by
   // side: three independent index -> hash -> key chains per iteration instead of one
 #pragma unroll 1
@@ -120,7 +112,10 @@ __device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_upda
     int f[3], key[3];
     unsigned slot[3];
 #pragma unroll
-    for (int g = 0; g < 3; ++g) f[g] = idx[(g * RLM_MAX_ACTIONS + a) * 32 + lane];
+    for (int g = 0; g < 3; ++g) {
+      const unsigned r = P.rg[g][a];
+      f[g] = h.null_state ? 0 : (pow2 ? (int)(((unsigned)h.s[g] + r) & mask) : mod_m(h.s[g] + r));
+    }
 #pragma unroll
     for (int g = 0; g < 3; ++g) { slot[g] = ut_hash(f[g]); key[g] = ut[slot[g]]; }
 #pragma unroll
@@ -332,8 +327,7 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
   double* V = (double*)scr;
   int* tt = (int*)(scr + ln_v_bytes(DBL ? 1 : 0));
   int* ut = tt + 2 * TT_SLOTS;
-  int* idx_s = ut + 2 * UT_SLOTS;
-  double* q_pre_a = (double*)(idx_s + 3 * RLM_MAX_ACTIONS * 32);
+  double* q_pre_a = (double*)(ut + 2 * UT_SLOTS);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   double* dec = q_pre_b + RLM_MAX_ACTIONS;
   const unsigned* rnd = rlm_rndseq_table;
@@ -407,10 +401,10 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
     LPH(2);
     if (DBL || GB != 27) {
       if (is_main) ln_tt_build(tt, ag, lane);
-      ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V, idx_s);
+      ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V);
     } else {
       double v[3 * RLM_MAX_ACTIONS];
-      ln_gather_issue<0, 27>(theta_a, h, v, idx_s, lane);
+      ln_gather_issue<0, 27>(theta_a, h, v);
       LPH(3);
       if (is_main) ln_tt_build(tt, ag, lane);  // under the gathers' round trip
       LPH(4);
@@ -477,7 +471,7 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
       steps_done++;
       LPH(13);
       if (!dbg_nopatch) {
-        if (local_patch) ln_patch_local(ut, scaled, idx_s, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
+        if (local_patch) ln_patch_local(ut, scaled, h, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
         else ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V);  // (long trace lists: read everything again)
       }
       LPH(14);
@@ -494,6 +488,13 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
     const int4* src = (const int4*)&ag;
     __stcg(dst + lane, src[lane]);
     if (lane + 32 < N16) __stcg(dst + lane + 32, src[lane + 32]);
+    // the env's next tick starts with the action selection (begin_step): its generator draw reads three words of the
+    // Mersenne Twister state in HBM -- ask L2 for them now instead of paying a DRAM round trip on lane 0 of the tick kernel
+    if (lane < 3 && ag.need_begin) {
+      int k = ag.mt_pol_idx; if (k >= 312) k -= 312;
+      int kk = k + (lane == 0 ? 0 : (lane == 1 ? 1 : 156)); if (kk >= 312) kk -= 312;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr.mt_pol + (size_t)env * 312 + kk));
+    }
   }
   __syncwarp();
   LPH(12);
@@ -907,6 +908,11 @@ __global__ void __launch_bounds__(32, 5) rlm_learn_staged_kernel(DevPtrs ptr, Dy
       const int4* src = (const int4*)&ag;
       __stcg(dst + lane, src[lane]);
       if (lane + 32 < N16) __stcg(dst + lane + 32, src[lane + 32]);
+      if (lane < 3 && ag.need_begin) {  // (see ln_step: the generator words of the next action selection)
+        int k = ag.mt_pol_idx; if (k >= 312) k -= 312;
+        int kk = k + (lane == 0 ? 0 : (lane == 1 ? 1 : 156)); if (kk >= 312) kk -= 312;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr.mt_pol + (size_t)env * 312 + kk));
+      }
     }
   }
   if (lane == 0 && (steps_done | sum_z)) {

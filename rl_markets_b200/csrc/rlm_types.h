@@ -97,7 +97,7 @@ struct EnvHdr {
   int run_id, run_pos;
   // Market::ToTicks of the last midprice (next_state_tail): the midprice moves on fewer than a third of the ticks
   double tk_px;
-  int tk_ticks, tk_pad;
+  int tk_ticks, tk_band;  // (tk_band: band of the last conversion, to_ticks' hint)
   float tx_px[RLM_TX_CAP];
   int tx_vol[RLM_TX_CAP];
   FillD tick_au, tick_bu;
@@ -110,6 +110,7 @@ struct VenueD {
   int cum_full[RLM_MAX_BANDS];   // ticks after fully traversing bands 0..k-1 (market.cpp:88-99 chain)
   int tts_tick[RLM_MAX_BANDS];   // Market::tts_ keys (market.cpp:27-37)
   double px[RLM_MAX_BANDS], ts[RLM_MAX_BANDS];
+  double inv_ts[RLM_MAX_BANDS];     // 1 / ts where ts is a power of two (x / ts == x * inv_ts exactly), else 0
   double cum_price[RLM_MAX_BANDS];  // price after fully traversing tts_ bands 0..k-1 (market.cpp:115-125 chain)
   long long open_lo, close_hi;      // IsOpen bounds: mo+30min, mc-30min (market.cpp:67-70)
 };

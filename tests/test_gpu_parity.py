@@ -136,6 +136,9 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
     ({"RLM_ROUNDS": "1", "RLM_ROUND_CAP": "2"}, "q_learn"),   # ... with at most two ticks per env and round
     ({"RLM_ROUNDS": "1", "RLM_ROUND_CAP": "1", "RLM_ROUND_STREAMS": "2"}, "sarsa"),
     ({"RLM_ENVW_WARPS": "2"}, "q_learn"),         # two envs per CTA of the warp-per-env tick kernel
+    ({"RLM_ROUNDS": "0"}, "q_learn"),             # tick-synchronous engine for every call (long calls default to rounds)
+    ({"RLM_ROUNDS": "0"}, "double_q_learn"),
+    ({"RLM_ROUNDS": "1"}, "r_learn"),             # (not part of the default: R-learning stays tick-synchronous)
 ])
 def test_every_engine_variant_matches_oracle(rlm, oracle, monkeypatch, env_vars, algo):
     """The non-default kernels (selected by environment variables read in rlm_create) are held to the same bar."""
