@@ -400,6 +400,8 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
   // small enough to be staged whole.
   if (cfg->n_envs > 16384 && !h->staged) h->agent_variant = 3;
   if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
+  // the one-warp learners pack (feature << 4 | action) into one word of their tile table (rlm_learn.cuh)
+  if (cfg->memory_size > (1LL << 27) && h->agent_variant == 4) h->agent_variant = 3;
   if (const char* s = getenv("RLM_GRAPHS")) h->use_graphs = atoi(s) != 0;
   if (const char* s = getenv("RLM_SUBBATCHES")) { const int v = atoi(s); if (v >= 1 && v <= RLM_MAX_SUB) h->n_sub = cfg->shared_policy ? 1 : v; }
   if (std::max(h->n_sub, h->round_streams) > 1) {
@@ -455,6 +457,10 @@ static int create_impl(const rlm_config* cfg, rlm_handle_s* h) {
     if (!getenv("RLM_ROUND_CAP")) h->dyn.round_cap = 3;
     if (const char* s = getenv("RLM_PDL")) rlm_set_pdl(atoi(s));  // programmatic dependent launch of the per-tick kernels (default off: slower when measured)
     if (const char* s = getenv("RLM_AGENT_VARIANT")) { const int v = atoi(s); h->agent_variant = (v == 1 || v == 3) ? v : 4; }
+    if (cfg->memory_size > (1LL << 27)) {  // (packed tile table of the one-warp learner step, also inside the fused engine)
+      if (h->agent_variant == 4) h->agent_variant = 3;
+      if (h->engine == 3) h->engine = 1;
+    }
   }
   // theta is gathered 8 bytes at a time from random addresses: do not let L2 promote misses to 64/128-byte fetches
   // (device-wide, and it stays for the lifetime of the hosting process)
@@ -781,12 +787,22 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
   int done = 0;
   // One CUDA graph per chunk instead of 2 * chunk launches: every node's parameters are fixed (the generator source has
   // no stream offset), so the instantiated graph is reused until alpha / epsilon / the mode change.
-  const bool graphs = h->use_graphs && h->graph_warm && S == 1 && !h->profile && h->cfg.source == RLM_SOURCE_GENERATOR;
+  const bool graphs = h->use_graphs && h->graph_warm && S == 1 && !h->profile;
+  const bool from_stream = h->cfg.source == RLM_SOURCE_STREAM;
   h->graph_warm = true;  // (the first call launches directly: function attributes are set outside any capture)
   while (graphs && done < n_ticks) {
     const int chunk = std::min(n_ticks - done, h->ready_cap);
     DynParams dt = d;
     dt.env0 = 0; dt.n_sub = B; dt.sub_idx = 0;
+    DevPtrs pg = h->ptr;
+    if (from_stream) {
+      // STREAM source: what changes from call to call (buffer, offset, length) goes through device memory, so that the
+      // graph of a chunk is reused by every call -- and by both buffers of the double-buffered upload
+      dt.ctl_stream = 1; dt.stream_off = 0; dt.stream_ticks = 0;
+      pg.stream = nullptr;
+      RunCtl rc = {++h->run_seq, n_ticks, d.stream_off + done, d.stream_ticks, h->ptr.stream, 0};
+      CK(rlm_launch_runctl(h->ptr, rc, h->stream));
+    }
     rlm_handle_s::TickGraph* tg = nullptr;
     for (auto& g : h->graphs)
       if (g.chunk == chunk && memcmp(&g.d, &dt, sizeof(DynParams)) == 0) tg = &g;
@@ -796,8 +812,8 @@ static int run_ticks_impl(rlm_handle h, int32_t n_ticks) {
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       cudaError_t ce = cudaMemsetAsync(h->ptr.ready_count, 0, (size_t)chunk * 4, h->stream);
       for (int t = 0; t < chunk && ce == cudaSuccess; ++t) {
-        ce = rlm_launch_env(h->ptr, dt, B, t, 0, h->env_variant, h->stream);
-        if (ce == cudaSuccess) ce = launch_agent_on(h, h->ptr, dt, t, 0, h->stream);
+        ce = rlm_launch_env(pg, dt, B, t, 0, h->env_variant, h->stream);
+        if (ce == cudaSuccess) ce = launch_agent_on(h, pg, dt, t, 0, h->stream);
       }
       cudaError_t ce2 = cudaStreamEndCapture(h->stream, &graph);
       if (ce != cudaSuccess || ce2 != cudaSuccess) { if (graph) cudaGraphDestroy(graph); CK(ce != cudaSuccess ? ce : ce2); }

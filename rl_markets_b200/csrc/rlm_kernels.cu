@@ -598,10 +598,19 @@ __global__ void __launch_bounds__(THREADS) rlm_env_kernel(DevPtrs ptr, DynParams
         if (P.source == RLM_SOURCE_GENERATOR) {
           flow_next_dev(&e.flow, &msg);
         } else {
-          const int pos = D.stream_off + tslot;  // tick-synchronous: every env consumes the same tick index
-          if (pos >= D.stream_ticks) { e.err |= ERR_STREAM_UNDERRUN; have = false; }
+          // tick-synchronous: every env consumes the same tick index.  Under a CUDA graph the call's stream pointer,
+          // offset and length are read from device memory (the graph outlives rlm_load_ticks and the run calls)
+          const rlm_tick_msg* sp = ptr.stream;
+          int s_off = D.stream_off, s_n = D.stream_ticks;
+          if (D.ctl_stream) {
+            const int4 rc4 = __ldg((const int4*)ptr.runctl);
+            s_off = rc4.z; s_n = rc4.w;
+            sp = (const rlm_tick_msg*)__ldg((const unsigned long long*)ptr.runctl + 2);
+          }
+          const int pos = s_off + tslot;
+          if (pos >= s_n) { e.err |= ERR_STREAM_UNDERRUN; have = false; }
           else {
-            const int4* src = (const int4*)(ptr.stream + ((size_t)pos * P.n_envs + b));
+            const int4* src = (const int4*)(sp + ((size_t)pos * P.n_envs + b));
             int4* dst = (int4*)&msg;
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = __ldg(src + i);
@@ -866,7 +875,16 @@ __global__ void __launch_bounds__(ENVW_WARPS * 32) rlm_env_kernel_w(DevPtrs ptr,
   int ready = -1;
   unsigned ticked = 0;
   if (e.ag.need_begin) begin_step_warp(e, ptr.mt_pol + (size_t)env * 312, D, w.flag, lane);
-  if (!only_begin && e.phase != PH_DONE) ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, D.stream_ticks, lane, ticked);
+  if (!only_begin && e.phase != PH_DONE) {
+    if (D.ctl_stream) {  // (see rlm_env_kernel: stream pointer, offset and length of this call live in *ptr.runctl)
+      const int4 rc4 = __ldg((const int4*)ptr.runctl);
+      DevPtrs pt = ptr;
+      pt.stream = (const rlm_tick_msg*)__ldg((const unsigned long long*)ptr.runctl + 2);
+      ready = envw_tick(w, ring, pt, D, env, rc4.z + tslot, rc4.w, lane, ticked);
+    } else {
+      ready = envw_tick(w, ring, ptr, D, env, D.stream_off + tslot, D.stream_ticks, lane, ticked);
+    }
+  }
   __syncwarp();
   envw_stage_out(g, &e, lane);
   if (!only_begin) KLOG_END(0);

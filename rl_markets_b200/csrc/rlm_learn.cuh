@@ -35,13 +35,13 @@ __host__ __device__ inline size_t ln_v_bytes(int is_double) { return (size_t)(is
 // feature -> eligibility of every weight this step's update moved (open addressing): the second evaluation of the step
 // adds the update to the weights it already holds instead of reading them back from L2 behind the reductions
 #ifndef UT_LOG2
-#define UT_LOG2 10
-#endif
+#define UT_LOG2 10  // 1024 slots, 512 entries per batch.  Measured: 256 or 512 slots cost more (longer probe chains in
+#endif               // every step's patch pass, extra batches on the launch's slowest warp) than the occupancy they buy
 #define UT_SLOTS (1 << UT_LOG2)
 #define UT_MAX_ENTRIES (UT_SLOTS / 2)
-// learner scratch of one step: [V][tile table 4096][update table 8 * UT_SLOTS][q_pre 2*9 doubles][dec 6 doubles]
+// learner scratch of one step: [V][tile table 2048][update table 8 * UT_SLOTS][q_pre 2*9 doubles][dec 6 doubles]
 __host__ __device__ inline size_t ln_scratch_bytes(int is_double) {
-  return (ln_v_bytes(is_double) + 2 * TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
+  return (ln_v_bytes(is_double) + TT_SLOTS * 4 + 2 * UT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48 + 15) & ~(size_t)15;
 }
 // per-warp shared memory of rlm_learn_kernel: [AgentD 704][scratch]
 __host__ __device__ inline size_t ln_warp_bytes(int is_double) { return (size_t)LN_AG_BYTES + ln_scratch_bytes(is_double); }
@@ -100,7 +100,9 @@ __device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every 
   ((float*)(ut + UT_SLOTS))[slot] = ev;
 }
 // the step's tile indices are re-derived from the hash sums (two instructions each for a power-of-two M): no index table
-__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, const LnSums& h, int lane, double* V) {
+__device__ __noinline__ void ln_patch_local(const int* ut, double scaled_update, unsigned long long s0, unsigned long long s1, unsigned long long s2,
+                                            bool null_state, int lane, double* V) {
+  ASSUME_SHARED(ut); ASSUME_SHARED(V);
   const int A = P.n_actions;
   const float* uv = (const float*)(ut + UT_SLOTS);
   const bool pow2 = P.m_pow2 != 0;
@@ -114,7 +116,8 @@ __device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_upda
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
       const unsigned r = P.rg[g][a];
-      f[g] = h.null_state ? 0 : (pow2 ? (int)(((unsigned)h.s[g] + r) & mask) : mod_m(h.s[g] + r));
+      const unsigned long long sg = g == 0 ? s0 : (g == 1 ? s1 : s2);
+      f[g] = null_state ? 0 : (pow2 ? (int)(((unsigned)sg + r) & mask) : mod_m(sg + r));
     }
 #pragma unroll
     for (int g = 0; g < 3; ++g) { slot[g] = ut_hash(f[g]); key[g] = ut[slot[g]]; }
@@ -190,15 +193,36 @@ __device__ __forceinline__ int ln_argmax(AgentD& ag, double v, const double* qs,
   return index;
 }
 
+// ---- tile -> last-writer table of the one-warp learners, ONE word per slot: (feature << 4) | action, empty = -1
+// (features < 2^27, at most 16 actions).  Same open addressing as tt_insert / tt_last_writer (rlm_agent.cuh) at half the
+// shared memory: 2 KB instead of 4, which is what lets a fourth CTA of three steps (a sixth staged table) share an SM.
+static_assert(RLM_MAX_ACTIONS <= 16, "packed tile table: four bits of action");
+__device__ __forceinline__ void ptt_insert(int* tt, int f, int a) {
+  const int packed = (f << 4) | a;
+  unsigned slot = tt_hash(f);
+  while (true) {
+    const int old = atomicCAS(&tt[slot], HS_EMPTY, packed);
+    if (old == HS_EMPTY) return;
+    if ((old >> 4) == f) { atomicMax(&tt[slot], packed); return; }  // same feature: the later (larger) action stays
+    slot = (slot + 1) & (TT_SLOTS - 1);
+  }
+}
+__device__ __forceinline__ int ptt_last_writer(const int* tt, int f) {
+  unsigned slot = tt_hash(f);
+  while (true) {
+    const int k = tt[slot];
+    if (k == HS_EMPTY) return -1;
+    if ((k >> 4) == f) return k & 15;
+    slot = (slot + 1) & (TT_SLOTS - 1);
+  }
+}
+
 // ---- Traces::decay + Traces::update + Agent::updateQ in one sweep (see trace_pass in rlm_agent.cuh for the
 // derivation); tt = tile -> last-writer table of the from-state, ut = update table (see ln_patch_local)
 __device__ __forceinline__ void ln_tt_build(int* tt, const AgentD& ag, int lane) {
   int4* t4 = (int4*)tt;
 #pragma unroll
-  for (int i = 0; i < 2 * TT_SLOTS / 4 / 32; ++i) {
-    const int k = lane + 32 * i;
-    t4[k] = (k < TT_SLOTS / 4) ? make_int4(HS_EMPTY, HS_EMPTY, HS_EMPTY, HS_EMPTY) : make_int4(-1, -1, -1, -1);
-  }
+  for (int i = 0; i < TT_SLOTS / 4 / 32; ++i) t4[lane + 32 * i] = make_int4(HS_EMPTY, HS_EMPTY, HS_EMPTY, HS_EMPTY);
   __syncwarp();
   if (!ag.null_from) {
     const int b0 = ag.from_base0[lane];
@@ -207,19 +231,23 @@ __device__ __forceinline__ void ln_tt_build(int* tt, const AgentD& ag, int lane)
     for (int a = 0; a < P.n_actions; ++a) {
       int f = b0 + P.ra_m[a];
       if (f >= M) f -= M;
-      tt_insert(tt, f, a);
+      ptt_insert(tt, f, a);
     }
   }
   __syncwarp();
 }
 
+// track: `ut` (cleared by the caller) takes the surviving entries, UT_MAX_ENTRIES at a time: when the table is full its
+// updates are added to the weights of the to-state right away (ln_patch_local on Vp; every feature is in the list once,
+// so every weight still gets at most one addition) and the table starts over.  The caller patches the last batch.
 __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, bool track, int* tf, float* te, double* theta, int action,
-                                          float rate, double scaled_update, int lane) {
+                                          float rate, double scaled_update, int lane, const LnSums& h, double* Vp) {
   const bool null_from = e.null_from != 0;
   const int b0 = e.from_base0[lane];
-  // track: `ut` (cleared by the caller) takes the surviving entries
   const float tol = 0.01f;
   int w = 0;
+  int ins = 0;  // entries in `ut` (warp-uniform)
+#define LN_UT_FLUSH() do { __syncwarp(); ln_patch_local(ut, scaled_update, h.s[0], h.s[1], h.s[2], h.null_state, lane, Vp); __syncwarp(); ut_clear(ut, lane); __syncwarp(); ins = 0; } while (0)
   if (rate != 0.0f) {
     const int n = e.n_traces;
 #pragma unroll 1
@@ -239,9 +267,10 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, 
           const int f = fq[k];
           const float ev = eq[k] * rate;
           bool keep = (i < n) && !(ev < tol);
-          if (keep) keep = (null_from ? (f == 0 ? P.n_actions - 1 : -1) : tt_last_writer(tt, f)) < 0;
+          if (keep) keep = (null_from ? (f == 0 ? P.n_actions - 1 : -1) : ptt_last_writer(tt, f)) < 0;
           const unsigned mask = __ballot_sync(FULL, keep);
           const int pos = w + __popc(mask & ((1u << lane) - 1u));
+          if (track && ins + __popc(mask) > UT_MAX_ENTRIES) LN_UT_FLUSH();
           if (keep) {
             __stcg(tf + pos, f);
             __stcg(te + pos, ev);
@@ -249,6 +278,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, 
             if (track) ut_insert(ut, f, ev);
           }
           w += __popc(mask);
+          ins += __popc(mask);
         }
       }
     }
@@ -259,7 +289,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, 
       f = b0 + P.ra_m[action];
       if (f >= (int)P.memory_size) f -= (int)P.memory_size;
     }
-    bool add = null_from ? (action == P.n_actions - 1) : (tt_last_writer(tt, f) == action);
+    bool add = null_from ? (action == P.n_actions - 1) : (ptt_last_writer(tt, f) == action);
     const unsigned same = __match_any_sync(FULL, f);
     add = add && ((__ffs(same) - 1) == lane);
     const unsigned mask = __ballot_sync(FULL, add);
@@ -270,6 +300,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, 
       add = add && (pos < P.trace_cap);
       total = P.trace_cap;
     }
+    if (track && ins + __popc(mask) > UT_MAX_ENTRIES) LN_UT_FLUSH();
     if (add) {
       __stcg(tf + pos, f);
       __stcg(te + pos, 1.0f);
@@ -278,6 +309,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, 
     }
     w = total;
   }
+#undef LN_UT_FLUSH
   __syncwarp();
   return w;
 }
@@ -326,7 +358,7 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
   LPH(0);
   double* V = (double*)scr;
   int* tt = (int*)(scr + ln_v_bytes(DBL ? 1 : 0));
-  int* ut = tt + 2 * TT_SLOTS;
+  int* ut = tt + TT_SLOTS;
   double* q_pre_a = (double*)(ut + 2 * UT_SLOTS);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   double* dec = q_pre_b + RLM_MAX_ACTIONS;
@@ -452,15 +484,16 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
     float* te = ptr.trace_e + (size_t)env * P.trace_cap;
     double* th = table ? theta_b : theta_a;
     if (stage == 1) th = table ? ptr.dtheta + P.memory_size : ptr.dtheta;  // accumulate, apply after the all-reduce
-    const bool local_patch = (stage == 0) && (ag.n_traces + 32 <= UT_MAX_ENTRIES);
+    const bool local_patch = (stage == 0) && !dbg_nopatch;
     if (local_patch) { ut_clear(ut, lane); __syncwarp(); }
-    const int nz = ln_trace_pass(ag, tt, ut, local_patch, tf, te, th, ag.cur_action, rate, scaled, lane);
+    const int nz = ln_trace_pass(ag, tt, ut, local_patch, tf, te, th, ag.cur_action, rate, scaled, lane, h,
+                                 V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
     if (lane == 0) { ag.n_traces = nz; ag.sum_traces += nz; ag.hs_valid = 0; }
     sum_z += (lane == 0) ? (unsigned long long)nz : 0ull;
     __syncwarp();
     LPH(8);
     // theta updates (L2 reductions) are ordered before re-reads: only the parity record and an overfull update table need them
-    if ((env < P.record_envs || (stage == 0 && !local_patch)) && !dbg_nofence) __threadfence();
+    if (env < P.record_envs && !dbg_nofence) __threadfence();
     LPH(9);
     if (env < P.record_envs) { if (RESIDENT) emit_record_res(ptr, hdr, env, ag, theta_a, ag.to_vars, lane); else emit_record_ool(ptr, g, env, ag, theta_a, ag.to_vars, lane); }
     if (stage == 0) {
@@ -470,10 +503,7 @@ __device__ __forceinline__ void ln_step(const DevPtrs& ptr, const DynParams& D, 
       if (lane == 0) { ag.prev_null = ag.null_from; ag.null_from = 0; ag.n_steps++; ag.ep_step++; ag.need_begin = 1; }
       steps_done++;
       LPH(13);
-      if (!dbg_nopatch) {
-        if (local_patch) ln_patch_local(ut, scaled, h, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));
-        else ln_gather<DBL, GB>(theta_a, theta_b, h, lane, V);  // (long trace lists: read everything again)
-      }
+      if (local_patch) ln_patch_local(ut, scaled, h.s[0], h.s[1], h.s[2], h.null_state, lane, V + (table ? RLM_MAX_ACTIONS * LN_VROW : 0));  // the last batch of updates
       LPH(14);
       __syncwarp();
       LPH(10);
@@ -514,9 +544,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32, LN_MIN_CTAS) rlm_learn_kernel(D
   const int n_ready = ptr.ready_count[tslot];
   unsigned long long steps_done = 0, sum_z = 0;
   if (n_ready > (int)blockIdx.x) KLOG_BEGIN(1);
-  // ready env k goes to warp (k / gridDim.x) of CTA (k % gridDim.x): a short list spreads over all SMs
+  // ready env k goes to warp (k / gridDim.x) of CTA (k % gridDim.x): a short list spreads evenly over all SMs.  (Measured:
+  // packing the list into the fewest CTAs instead -- every working CTA with all its warps at work -- leaves some SMs with
+  // 12 steps and others with 8, and the launch waits for the fullest SM: 82 us instead of 75.)
+  const int C = gridDim.x;
 #pragma unroll 1
-  for (int idx = warp * gridDim.x + blockIdx.x; idx < n_ready; idx += LN_WARPS * gridDim.x)
+  for (int idx = warp * C + blockIdx.x; idx < n_ready; idx += LN_WARPS * C)
     ln_step<DBL, false, 27>(ptr, D, ptr.ready[idx], *(AgentD*)wsm, wsm + LN_AG_BYTES, nullptr, lane, stage, steps_done, sum_z, idx);
   if (steps_done) KLOG_END(1);
   if (lane == 0 && (steps_done | sum_z)) {
@@ -683,7 +716,7 @@ cudaError_t rlm_launch_fused2(const DevPtrs& ptr, const DynParams& D, int n_envs
 // the sums the L2 reduction would have produced), and the second evaluation simply walks the updated table -- no
 // gathers, no reductions, no fence, no patching.  One warp per CTA, one CTA per ready env at a time.
 #define LS_IROW 104  // u16 tile indices per action row (96 used; 16-byte aligned rows)
-__host__ __device__ inline size_t ls_fixed_bytes() { return 16 + LN_AG_BYTES + (size_t)RLM_MAX_ACTIONS * LS_IROW * 2 + 2 * TT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48; }
+__host__ __device__ inline size_t ls_fixed_bytes() { return 16 + LN_AG_BYTES + (size_t)RLM_MAX_ACTIONS * LS_IROW * 2 + TT_SLOTS * 4 + 8 * 2 * RLM_MAX_ACTIONS + 48; }
 __host__ __device__ inline size_t ls_smem_bytes(long long memory_size) { return ((ls_fixed_bytes() + 15) & ~(size_t)15) + (size_t)memory_size * 8; }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -719,14 +752,14 @@ __device__ __noinline__ double ls_sums(const double* tab, const unsigned short* 
   return (lane < P.n_actions) ? ls_chain(tab, idx + lane * LS_IROW) : 0.0;
 }
 
-__global__ void __launch_bounds__(32, 5) rlm_learn_staged_kernel(DevPtrs ptr, DynParams D, int tslot) {
+__global__ void __launch_bounds__(32, 6) rlm_learn_staged_kernel(DevPtrs ptr, DynParams D, int tslot) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x;
   unsigned long long* mbar = (unsigned long long*)smem;
   AgentD& ag = *(AgentD*)(smem + 16);
   unsigned short* idx_s = (unsigned short*)(smem + 16 + LN_AG_BYTES);
   int* tt = (int*)(idx_s + RLM_MAX_ACTIONS * LS_IROW);
-  double* q_pre_a = (double*)(tt + 2 * TT_SLOTS);
+  double* q_pre_a = (double*)(tt + TT_SLOTS);
   double* q_pre_b = q_pre_a + RLM_MAX_ACTIONS;
   double* dec = q_pre_b + RLM_MAX_ACTIONS;
   double* tab = (double*)(smem + ((ls_fixed_bytes() + 15) & ~(size_t)15));
@@ -848,7 +881,7 @@ __global__ void __launch_bounds__(32, 5) rlm_learn_staged_kernel(DevPtrs ptr, Dy
               const int f = fq[k];
               const float ev = eq[k] * rate;
               bool keep = (i < n) && !(ev < 0.01f);
-              if (keep) keep = (null_from ? (f == 0 ? A - 1 : -1) : tt_last_writer(tt, f)) < 0;
+              if (keep) keep = (null_from ? (f == 0 ? A - 1 : -1) : ptt_last_writer(tt, f)) < 0;
               const unsigned mask = __ballot_sync(FULL, keep);
               const int pos = w + __popc(mask & ((1u << lane) - 1u));
               if (keep) {
@@ -869,7 +902,7 @@ __global__ void __launch_bounds__(32, 5) rlm_learn_staged_kernel(DevPtrs ptr, Dy
           f = ag.from_base0[lane] + P.ra_m[action];
           if (f >= (int)P.memory_size) f -= (int)P.memory_size;
         }
-        bool add = null_from ? (action == A - 1) : (tt_last_writer(tt, f) == action);
+        bool add = null_from ? (action == A - 1) : (ptt_last_writer(tt, f) == action);
         const unsigned same = __match_any_sync(FULL, f);
         add = add && ((__ffs(same) - 1) == lane);
         const unsigned mask = __ballot_sync(FULL, add);

@@ -153,6 +153,7 @@ struct DynParams {  // changes between launches (HandleTerminal / GoGreedy)
   int debug_flags;    // RLM_TIMING build only (RLM_DEBUG_FLAGS): what-if switches of tools/timeline_probe.py; results are wrong with any set
   int env_hash;       // tick kernel hashes the to-state and prefetches its tiles at a step end (RLM_ENV_HASH=1; measured slower)
   int round_cap;      // round-paced engine: most ticks an env runs in one round (RLM_ROUND_CAP; 0 = up to its step end)
+  int ctl_stream;     // tick-synchronous engine under a CUDA graph, STREAM source: stream pointer / offset / length come from *DevPtrs::runctl
   int hold;           // split surface (rlm_env_step): envs whose step has ended, or whose next action is not applied yet, do not tick
 };
 
