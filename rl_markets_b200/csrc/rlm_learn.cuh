@@ -100,9 +100,8 @@ __device__ __forceinline__ void ut_insert(int* ut, int f, float ev) {  // every 
   ((float*)(ut + UT_SLOTS))[slot] = ev;
 }
 // the step's tile indices are re-derived from the hash sums (two instructions each for a power-of-two M): no index table
-__device__ __noinline__ void ln_patch_local(const int* ut, double scaled_update, unsigned long long s0, unsigned long long s1, unsigned long long s2,
-                                            bool null_state, int lane, double* V) {
-  ASSUME_SHARED(ut); ASSUME_SHARED(V);
+__device__ __forceinline__ void ln_patch_local(const int* ut, double scaled_update, unsigned long long s0, unsigned long long s1, unsigned long long s2,
+                                               bool null_state, int lane, double* V) {
   const int A = P.n_actions;
   const float* uv = (const float*)(ut + UT_SLOTS);
   const bool pow2 = P.m_pow2 != 0;
@@ -130,6 +129,13 @@ __device__ __noinline__ void ln_patch_local(const int* ut, double scaled_update,
       }
     }
   }
+}
+
+// (the rare mid-list drain of a full table calls this copy; the step's final batch is patched inline)
+__device__ __noinline__ void ln_patch_local_ool(const int* ut, double scaled_update, unsigned long long s0, unsigned long long s1, unsigned long long s2,
+                                                bool null_state, int lane, double* V) {
+  ASSUME_SHARED(ut); ASSUME_SHARED(V);
+  ln_patch_local(ut, scaled_update, s0, s1, s2, null_state, lane, V);
 }
 
 // ---- exact-order sum of agent.cpp:117-135 over one action row of raw weights: 16 blocks of 8; block b+1 is loaded
@@ -247,7 +253,7 @@ __device__ __forceinline__ int ln_trace_pass(AgentD& e, const int* tt, int* ut, 
   const float tol = 0.01f;
   int w = 0;
   int ins = 0;  // entries in `ut` (warp-uniform)
-#define LN_UT_FLUSH() do { __syncwarp(); ln_patch_local(ut, scaled_update, h.s[0], h.s[1], h.s[2], h.null_state, lane, Vp); __syncwarp(); ut_clear(ut, lane); __syncwarp(); ins = 0; } while (0)
+#define LN_UT_FLUSH() do { __syncwarp(); ln_patch_local_ool(ut, scaled_update, h.s[0], h.s[1], h.s[2], h.null_state, lane, Vp); __syncwarp(); ut_clear(ut, lane); __syncwarp(); ins = 0; } while (0)
   if (rate != 0.0f) {
     const int n = e.n_traces;
 #pragma unroll 1
@@ -558,7 +564,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, LN_MIN_CTAS) rlm_learn_kernel(D
   }
 }
 
-cudaError_t rlm_launch_learn(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int tslot, int n_sms, int stage, cudaStream_t st) {
+cudaError_t rlm_launch_learn(const DevPtrs& ptr, const DynParams& D, int n_envs, int is_double, int tslot, int n_sms, int stage, int expected_steps, cudaStream_t st) {
   const size_t smem = LN_WARPS * ln_warp_bytes(is_double);
   static size_t attr_smem[2] = {0, 0};
   if (smem > attr_smem[is_double ? 1 : 0]) {
@@ -583,6 +589,9 @@ cudaError_t rlm_launch_learn(const DevPtrs& ptr, const DynParams& D, int n_envs,
   if (per_sm_cap < 0) { const char* e = getenv("RLM_LEARN_CTAS_PER_SM"); per_sm_cap = e ? atoi(e) : 0; }
   int ps = per_sm[is_double ? 1 : 0];
   if (per_sm_cap > 0 && per_sm_cap < ps) ps = per_sm_cap;
+  // no more CTAs per SM than the steps this launch usually finds need (measured at C1, ~1 200 steps per tick: 3 CTAs per
+  // SM 74.4 us, 4 CTAs 75.6 us; a round's ~2 300 steps want all four)
+  if (expected_steps > 0) ps = std::max(1, std::min(ps, (expected_steps + LN_WARPS * n_sms - 1) / (LN_WARPS * n_sms)));
   const int cap = n_sms * ps;
   if (grid > cap) grid = cap;
   if (is_double) rlm_learn_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(ptr, D, tslot, stage);
