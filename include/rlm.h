@@ -175,9 +175,12 @@ int rlm_new_env(rlm_handle h, const rlm_flow_params* flow);
  * The copy is issued on the handle's copy stream; the buffer must stay valid until rlm_sync. */
 int rlm_load_ticks(rlm_handle h, const rlm_tick_msg* msgs, int32_t n_ticks);
 
-/* Advance every env by n_ticks market ticks (tick-synchronous).  Each env runs
- * warm-up, performAction's inner NextState loop, and -- whenever its midprice
- * has moved -- the complete learner step. Asynchronous; see rlm_sync. */
+/* Advance every env by n_ticks market ticks.  Each env runs warm-up, performAction's inner NextState loop, and --
+ * whenever its midprice has moved -- the complete learner step.  On return every env has consumed exactly n_ticks
+ * messages and sits inside performAction's loop, whatever order the engine ran the envs' ticks in (they never interact).
+ * Calls shorter than 128 ticks only enqueue work (asynchronous; see rlm_sync); longer calls of independent policies on
+ * up to 16 384 envs run round by round and return when the device is nearly done with them (the host follows the
+ * device to learn when the last env has finished; RLM_ROUNDS=0 keeps every call asynchronous). */
 int rlm_run_ticks(rlm_handle h, int32_t n_ticks);
 
 int rlm_sync(rlm_handle h);

@@ -20,6 +20,13 @@
 __constant__ DevParams P;
 
 #define LLMIN ((long long)0x8000000000000000ull)
+// per-level loops of the book code: unrolled (five copies, independent loads in flight) or rolled (a fifth of the code:
+// this kernel's straight-line footprint is what its instruction fetch stalls on)
+#ifdef RLM_ROLL_LEVELS
+#define LEVEL_UNROLL _Pragma("unroll 1")
+#else
+#define LEVEL_UNROLL _Pragma("unroll")
+#endif
 
 // ---------------------------------------------------------------- utilities/comparison.h:13-16
 __device__ __forceinline__ double pkey(double p) { return rint(p * 10000.0); }
@@ -137,7 +144,7 @@ __device__ long long side_volume(const SideD& s, double price) {  // book.cpp:20
   if (!s.has_cur) return 0;
   double k = pkey(price);
   long long v = 0;
-#pragma unroll
+  LEVEL_UNROLL
   for (int l = 0; l < RLM_DEPTH; ++l)
     if (pkey(s.px[l]) == k) v = s.vol[l];
   return v;
@@ -146,7 +153,7 @@ __device__ long long side_last_volume(const SideD& s, double price) {  // book.c
   if (!s.has_last) return 0;
   double k = pkey(price);
   long long v = 0;
-#pragma unroll
+  LEVEL_UNROLL
   for (int l = 0; l < RLM_DEPTH; ++l)
     if (pkey(s.last_px[l]) == k) v = s.last_vol[l];
   return v;
@@ -190,7 +197,7 @@ __device__ __noinline__ void side_update_order(SideD& s, long long transaction_v
 
 // Book::StashState (book.cpp:50-55)
 __device__ __forceinline__ void side_stash(SideD& s) {
-#pragma unroll
+  LEVEL_UNROLL
   for (int l = 0; l < RLM_DEPTH; ++l) { s.last_px[l] = s.px[l]; s.last_vol[l] = s.vol[l]; }
   s.has_last = s.has_cur;
   s.last_total_vol = s.total_vol;
@@ -199,7 +206,7 @@ __device__ __forceinline__ void side_stash(SideD& s) {
 // tpx/tvol/n_tx: the tick's aggregated prints (the `transactions` map handed through UpdateBookProfiles).
 __device__ __forceinline__ void side_apply_row(SideD& s, const float* px, const int* vol, const float* tpx, const int* tvol, int n_tx, int* err) {
   long long tv = s.total_vol;
-#pragma unroll
+  LEVEL_UNROLL
   for (int l = 0; l < RLM_DEPTH; ++l) {
     double p = (double)px[l];
     int v = vol[l];

@@ -17,7 +17,7 @@ def _line(name):
 
 
 def test_committed_headline_line_has_every_contract_key():
-    d = _line("bench_r2_c1.json")
+    d = _line("bench_r2b_c1.json")
     assert BASE_KEYS <= set(d) and {"roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches", "extra"} <= set(d)
     assert d["metric"].startswith("env steps/sec") and d["unit"] == "env_steps/s" and d["n_gpus"] == 1
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f64"
@@ -35,7 +35,12 @@ def test_committed_headline_line_has_every_contract_key():
     assert e["distinct_streams"] == 4096, "every env gets its own host-generated stream"
     assert e["value"] != d["value"], "the end-to-end figure must be measured, not copied"
     ticks = d["config"]["ticks_per_bench_step"]
-    assert d["gpu_launches"] >= 2 * ticks * d["steps"]  # two kernels per market tick
+    # two kernels per market tick (tick-synchronous) or per round of at most three ticks (round-paced engine, long calls)
+    assert d["gpu_launches"] >= 2 * ticks * d["steps"] // (3 if "round" in d["config"]["engine"] else 1)
+    # the roofline block is on the dominant kernel, timed live with CUDA events around its launches
+    assert r["avg_launch_ms"] > 0 and abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert 0.5 <= r["share_of_tick_kernel_time"] < 1.0 and r["other_kernel"]["avg_launch_ms"] > 0
+    assert r["whole_path"]["achieved"] > 0 and abs(r["whole_path"]["achieved"] - d["value"] * r["whole_path"]["algorithmic_bytes_per_env_step"] / 1e9) < 1e-6 * r["whole_path"]["achieved"]
     assert d["ms_per_step"] * d["steps"] >= 1000.0, "the timed region is at least a second long"
     assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.9 * d["clocks"]["sm_max_mhz"]
     assert d["config"]["pretrain_ticks"] > 0 and d["config"]["theta_nonzero_fraction_at_start"] > 0.5  # long-run tables
@@ -44,12 +49,12 @@ def test_committed_headline_line_has_every_contract_key():
 
 
 def test_committed_scaling_and_reference_lines():
-    two = _line("bench_r2_c1_2gpu.json")
-    one = _line("bench_r2_c1.json")
+    two = _line("bench_r2b_c1_2gpu.json")
+    one = _line("bench_r2b_c1.json")
     assert two["n_gpus"] == 2 and 1.8 < two["value"] / one["value"] < 2.2
     assert two["extra"]["C3"]["value"] > 0 and "shared theta" in two["extra"]["C3"]["policy"]
     assert two["extra"]["C4"]["value"] > 0 and two["extra"]["C4"]["workload"].startswith("C4: 131072")
-    ref = _line("bench_r2_c1_reference_arm.json")
+    ref = _line("bench_r2b_c1_reference_arm.json")
     assert ref["impl"] == "reference" and BASE_KEYS <= set(ref)
     assert ref["config"]["workload"] == one["config"]["workload"], "both arms name the same workload"
     assert ref["e2e"]["value"] == ref["value"] and ref["e2e"]["h2d_bytes_per_step"] == 0
