@@ -1,14 +1,20 @@
 // rlm_kernels.cu -- sm_100a kernels of the batched LOB environment + tile-coded TD agent.
 //
-// Two launches per market tick, tick-synchronous over all envs of the handle (the default engine):
+// Two kernels, driven by two engines (rlm_api.cu: run_ticks_impl / run_rounds); per env both run the same sequence
+// begin_step / tick / ... / learner step, so their results are bit-identical:
+//   tick-synchronous  two launches per market tick over all envs of the handle (short run calls, large batches, shared
+//                     policies, backtest, the split surface), one CUDA graph per chunk of ticks;
+//   round-paced       two launches per ROUND (the default for long run calls of up to 16 384 independent envs): every
+//                     live env runs up to DynParams::round_cap of its own ticks, until its step ends.
 //
-//   env tick     rlm_env_kernel_w: one WARP per env (B <= 16384) -- record staged in shared memory, Philox draws
-//                on three lanes, ask/bid book updates on two, rolling windows and state variables one per lane,
-//                the rest of the scalar market logic (Intraday::NextState, src/environment/intraday.cpp:224-272,
-//                and rlm_env.cuh) on lane 0.  rlm_env_kernel<32>: one THREAD per env (B > 16384), the record in
-//                lane-interleaved local memory, SIMT over 32 envs.  An env whose midprice moved
-//                (Base::performAction's do-while, base.cpp:285-305) finishes the step, writes its state
-//                variables and reward, and appends itself to the tick's ready list.
+//   env tick     rlm_env_kernel_w / rlm_env_round_kernel: one WARP per env (B <= 16384) -- record staged in shared
+//                memory, Philox draws on three lanes, the generator's book update one level per lane, ask/bid book
+//                updates on two lanes, rolling windows and state variables one per lane (their ToTicks conversions in
+//                two convergent passes), quote placement at a step start on two lanes, the rest of the scalar market
+//                logic (Intraday::NextState, src/environment/intraday.cpp:224-272, and rlm_env.cuh) on lane 0.
+//                rlm_env_kernel<32>: one THREAD per env (B > 16384), the record in lane-interleaved local memory, SIMT
+//                over 32 envs.  An env whose midprice moved (Base::performAction's do-while, base.cpp:285-305)
+//                finishes the step, writes its state variables and reward, and appends itself to the ready list.
 //   learner step rlm_learn_kernel (rlm_learn.cuh): ONE warp per ready env (lane j = tiling j of all three feature
 //                groups, N_TILINGS == 32 == warp width): tile hashing, theta gathers, exact-order Q sums, the fused
 //                trace-decay/clear/set/theta-update pass (Agent::HandleTransition, src/rl/agent.cpp:86-101) and
@@ -17,10 +23,10 @@
 //                rlm_agent3_kernel (round 1: one CTA of three warps per env, warp g = feature group g) serves the
 //                R-learning agents, the backtest step and batches above 16 384 envs; rlm_agent_kernel<8> is older still.
 //
-// The next tick's env kernel starts each stepped env with Learner::_step's action selection and DoAction
-// (serial.cpp:55-61, base.cpp:254-284), which is scalar work again.  Alternative engines, all parity-green and all
-// slower on a B200: rlm_env_round_kernel (round-paced: every env ticks to its next step end),
-// rlm_fused2_kernel (rlm_learn.cuh), rlm_run_kernel (persistent queue) and rlm_fused_kernel (RLM_ENGINE=F|p|f).
+// The next tick of a stepped env starts with Learner::_step's action selection and DoAction (serial.cpp:55-61,
+// base.cpp:254-284; begin_step / begin_step_warp).  Alternative engines, all parity-green and all slower on a B200
+// (DESIGN.md section 3.5): rlm_fused2_kernel (rlm_learn.cuh), rlm_run_kernel (persistent queue) and rlm_fused_kernel
+// (RLM_ENGINE=F|p|f).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #define RLM_TABLE_QUAL static __device__ const

@@ -119,6 +119,68 @@ def test_stream_mode_equals_generator_mode(rlm, oracle):
     mg.close()
 
 
+def test_run_calls_of_mixed_lengths_switch_engines_without_a_trace(rlm):
+    """Short calls run tick by tick, long ones round by round (rlm_run_ticks picks per call): any split of the same ticks
+    must leave the same records, weights and counters."""
+    n_envs, M = 7, 8192
+    res = []
+    for split in ([1200], [100, 300, 64, 536, 200], [127, 128, 129, 816]):
+        y, cfg = _mk("sarsa", M, n_envs, flow_seed=31, rec_cap=700)
+        m = rlm.BatchedMarket(cfg)
+        for n in split:
+            m.run_ticks(n)
+        m.sync()
+        c = m.counters()
+        recs = [m.records(b) for b in range(n_envs)]  # (list, backing array) per env
+        res.append((c.steps, c.ticks, [bytes(m.theta(b)) for b in range(n_envs)], recs))
+        m.close()
+    assert res[0][0] > 100
+    for other in res[1:]:
+        assert other[:3] == res[0][:3]
+        for b in range(n_envs):
+            ra, rb = res[0][3][b][0], other[3][b][0]
+            assert len(ra) == len(rb) > 10
+            for i in range(len(ra)):
+                assert not abi.record_fields_equal(ra[i], rb[i]), "env %d step %d" % (b, i)
+
+
+@pytest.mark.parametrize("env_vars,call_ticks", [({}, 50), ({"RLM_ENV_VARIANT": "1"}, 50), ({"RLM_ROUNDS": "0"}, 250), ({}, 125)])
+def test_stream_mode_in_short_run_calls(rlm, monkeypatch, env_vars, call_ticks):
+    """Run calls shorter than 128 ticks stay tick-synchronous and -- from the second call on -- replay ONE CUDA graph per
+    chunk length whose stream pointer / offset / length live in device memory: many calls per loaded chunk, chunk swaps
+    (double-buffered uploads) in between, both tick kernels.  Must equal the generator run bit for bit."""
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, v)
+    n_envs, n_ticks, chunk = 6, 1500, 500
+    y, cfg = _mk("q_learn", 8192, n_envs, flow_seed=11, rec_cap=800, source=abi.SOURCE_STREAM)
+    msgs = (abi.TickMsg * (n_ticks * n_envs))()
+    for b in range(n_envs):
+        one = rlm.flow_generate(cfg.flow, b, 0, n_ticks)
+        for t in range(n_ticks):
+            msgs[t * n_envs + b] = one[t]
+    ms = rlm.BatchedMarket(cfg)
+    base, per_tick = C.addressof(msgs), n_envs * C.sizeof(abi.TickMsg)
+    for c0 in range(0, n_ticks, chunk):
+        ms.load_ticks(base + c0 * per_tick, chunk)
+        for _ in range(chunk // call_ticks):
+            ms.run_ticks(call_ticks)
+    ms.sync()
+    y2, cfg2 = _mk("q_learn", 8192, n_envs, flow_seed=11, rec_cap=800, source=abi.SOURCE_GENERATOR)
+    mg = rlm.BatchedMarket(cfg2)
+    mg.run_ticks(n_ticks)
+    mg.sync()
+    assert ms.counters().steps == mg.counters().steps > 0
+    for b in range(n_envs):
+        rs, _k1 = ms.records(b)
+        rg, _k2 = mg.records(b)
+        assert len(rs) == len(rg) and len(rs) > 50
+        for i in range(len(rs)):
+            assert not abi.record_fields_equal(rs[i], rg[i]), "env %d step %d" % (b, i)
+        assert bytes(ms.theta(b)) == bytes(mg.theta(b))
+    ms.close()
+    mg.close()
+
+
 @pytest.mark.parametrize("env_vars,algo", [
     ({"RLM_ENV_VARIANT": "1"}, "q_learn"),        # thread-per-env tick kernel (default for B > 16384)
     ({"RLM_AGENT_VARIANT": "1"}, "q_learn"),      # one-warp-per-env learner kernel
