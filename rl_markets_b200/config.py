@@ -159,7 +159,15 @@ def from_dict(y, n_envs=1, ticker=None, device=0, env_index0=0, shared_policy=Fa
     c.tp_lookback = int(_get(y, ("market", "target_price", "lookback"), 1))
     lat = _get(y, ("market", "latency", "type"), "fixed")
     if lat not in ("fixed", "normal", "lognormal"):
-        raise ValueError("Unknown latency type: " + str(lat))  # base.cpp:94-95 (latency itself is dead code)
+        raise ValueError("Unknown latency type: " + str(lat))  # base.cpp:94-95
+    # The sampler itself is not built: its only consumer writes Intraday::ref_time (intraday.cpp:178), which nothing reads,
+    # and it draws from a generator of its own (latency.cpp:19-22) -- no observable effect.  Its constructor checks are kept.
+    if float(_get(y, ("market", "latency", "floor"), 0.0)) < 0.0:
+        raise ValueError("Latency must be zero or positive.")  # latency.cpp:12-13
+    if lat == "normal" and _get(y, ("market", "latency", "sigma"), None) is None:
+        raise ValueError("market.latency.sigma is required for the normal latency (base.cpp:86)")
+    if lat == "lognormal" and _get(y, ("market", "latency", "beta"), None) is None:
+        raise ValueError("market.latency.beta is required for the lognormal latency (base.cpp:91)")
     # venue
     if ticker is None:
         syms = _get(y, ("data", "symbols"), ["AAL.L"])

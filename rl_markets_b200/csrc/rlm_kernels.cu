@@ -35,6 +35,7 @@
 #include "rlm_agent.cuh"
 #include <cstdio>
 #include "rlm_kernels.h"
+#define RLM_ENVT_CARVEOUT_DEFAULT 30  // measured: 88 -> 30 takes the thread-per-env tick kernel from 643 to 533 us at C4, 356 to 291 us at C2 (0: 549 / 367)
 #define RLM_SMEM_CARVEOUT 88  // percent of the 228 KB L1/shared array configured as shared memory, for every per-tick kernel
 
 // ---- one-warp-per-env learner (rlm_agent_kernel, fused and persistent engines): per warp [AgentD][scratch]
@@ -1989,12 +1990,26 @@ static int envw_warps_per_cta() {
   }
   return w;
 }
+// L1 / shared-memory split of the warp-per-env tick kernels (percent shared; RLM_ENVW_CARVEOUT).  They need 79 KB per SM
+// (four CTAs); the rest is better spent as L1 -- measured at C1 against the learner's 88 %: tick kernel 36.7 -> 35.3 us,
+// end to end +2 % -- even though the SMs are then reconfigured between the two kernels of a tick.
+static int envw_carveout() {
+  static int c = -1;
+  if (c < 0) { c = 40; if (const char* e = getenv("RLM_ENVW_CARVEOUT")) { const int v = atoi(e); if (v >= 35 && v <= 100) c = v; } }
+  return c;
+}
 cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, int tslot, int only_begin, int variant, cudaStream_t st) {
   if (D.n_sub > 0) n_envs = D.n_sub;  // one sub-batch
   if (variant == 1) {  // one thread per env (SIMT over envs)
     const int T = 32;
     static bool attr1 = false;
-    if (!attr1) { cudaFuncSetAttribute(rlm_env_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT); attr1 = true; }
+    if (!attr1) {
+      // this kernel uses no shared memory at all; its per-thread record copy lives in local memory, i.e. in L1 (RLM_ENVT_CARVEOUT)
+      int c = RLM_ENVT_CARVEOUT_DEFAULT;
+      if (const char* e = getenv("RLM_ENVT_CARVEOUT")) { const int v = atoi(e); if (v >= 0 && v <= 100) c = v; }
+      cudaFuncSetAttribute(rlm_env_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+      attr1 = true;
+    }
     rlm_env_kernel<T><<<(n_envs + T - 1) / T, T, 0, st>>>(ptr, D, tslot, only_begin);
     return cudaGetLastError();
   }
@@ -2008,7 +2023,7 @@ cudaError_t rlm_launch_env(const DevPtrs& ptr, const DynParams& D, int n_envs, i
     }
     // the same L1/shared split as the learner kernel: CTAs of the two kernels (different sub-batches, different streams)
     // can then share an SM instead of waiting for it to drain and be reconfigured
-    cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
+    cudaFuncSetAttribute(rlm_env_kernel_w, cudaFuncAttributePreferredSharedMemoryCarveout, envw_carveout());
     attr = true;
   }
   return launch_pdl(rlm_env_kernel_w, (n_envs + W - 1) / W, W * 32, smem, st, ptr, D, tslot, only_begin);
@@ -2023,7 +2038,7 @@ cudaError_t rlm_launch_env_round(const DevPtrs& ptr, const DynParams& D, int n_e
       cudaError_t e = cudaFuncSetAttribute(rlm_env_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    cudaFuncSetAttribute(rlm_env_round_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RLM_SMEM_CARVEOUT);
+    cudaFuncSetAttribute(rlm_env_round_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, envw_carveout());
     attr = true;
   }
   return launch_pdl(rlm_env_round_kernel, (n_envs + W - 1) / W, W * 32, smem, st, ptr, D, tslot);

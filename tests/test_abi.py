@@ -85,6 +85,14 @@ def test_config_quirks_of_the_reference():
         config.from_dict(config.example_dict(**{"state.variables": ["pos", "bogus", "spd", "vol"]}))
     with pytest.raises(ValueError):
         config.from_dict(config.example_dict(), ticker="AAL.XX")
+    # market.latency (base.cpp:77-99, latency.cpp:9-14): the three types are accepted (the sample is dead upstream:
+    # intraday.cpp:178 writes ref_time, nothing reads it), the constructor checks are mirrored
+    for lat in ({"market.latency.type": "normal", "market.latency.sigma": 1.0, "market.latency.mu": 2.0},
+                {"market.latency.type": "lognormal", "market.latency.beta": 0.5}, {"market.latency.floor": 3.0}):
+        config.from_dict(config.example_dict(**lat))
+    for bad in ({"market.latency.type": "uniform"}, {"market.latency.floor": -1.0}, {"market.latency.type": "lognormal"}):
+        with pytest.raises(ValueError):
+            config.from_dict(config.example_dict(**bad))
 
 
 def test_no_cpu_fallback():
